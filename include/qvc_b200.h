@@ -1,0 +1,252 @@
+/*
+ * qvc_b200.h -- C ABI of libqvc_b200.so: the B200 (sm_100a) implementation of QuickVC's
+ * conversion forward pass, `SynthesizerTrn.infer` (/root/reference/models.py:625-642).
+ *
+ * The reference has no native boundary at all (it is pure PyTorch); the only interface for this
+ * path is the Python method `SynthesizerTrn.infer(unit, mel)`.  This header is the boundary a
+ * binding for that method sits on: plain pointers, sizes and a cudaStream_t, no torch types.
+ * The Python mirror of the reference class lives in quickvc-official_b200/models.py and calls
+ * these entry points through ctypes; INTEGRATION.md shows the stub a maintainer of the reference
+ * would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative qvc_status; qvc_last_error() returns a
+ *     thread-local description of the last failure;
+ *   - no function allocates device memory: the caller passes weights, workspace and outputs;
+ *   - all work is enqueued on the caller's stream; functions are re-entrant across streams as long
+ *     as each stream uses its own workspace;
+ *   - activations inside the library are "series-major": [utterance][frame][channel], channel
+ *     contiguous; the public tensors keep the reference layout (B, C, T).
+ */
+#ifndef QVC_B200_H_
+#define QVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QVC_ABI_VERSION 1
+
+typedef struct CUstream_st* qvc_stream_t;   /* == cudaStream_t */
+
+typedef enum {
+  QVC_OK = 0,
+  QVC_ERR_ARG = -1,        /* bad argument (shape, alignment, null pointer)                  */
+  QVC_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed                            */
+  QVC_ERR_NO_DEVICE = -3,  /* no sm_100 device / driver                                       */
+  QVC_ERR_WORKSPACE = -4,  /* workspace too small                                             */
+  QVC_ERR_UNSUPPORTED = -5 /* configuration outside what the kernels were built for           */
+} qvc_status;
+
+/* Operand format of the convolution GEMM operands (activations as stored between layers, and the
+ * folded weights).  Accumulation is always fp32. */
+typedef enum {
+  QVC_OPF_F32 = 0,   /* unrounded fp32 operands; exact-fp32 FMA kernels only                  */
+  QVC_OPF_TF32 = 1,  /* fp32 storage, values rounded-to-nearest to TF32 by the producer       */
+  QVC_OPF_BF16 = 2   /* bf16 storage                                                          */
+} qvc_opformat;
+
+typedef enum {
+  QVC_BACKEND_FMA = 0,     /* CUDA-core fp32 FMA kernels (exact fp32; validation / strict mode) */
+  QVC_BACKEND_TCGEN05 = 1  /* tcgen05 tensor-core implicit-GEMM kernels fed by TMA              */
+} qvc_backend;
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic series convolution -- the building block behind every Conv1d / ConvTranspose1d on the
+ * path (modules.py:64,67,134-143,193,195; models.py:71,73,327-335,346).
+ *
+ *   acc[b][t][n] = sum_{j<k} sum_{c<cin} w[n][j][c] * x[b][t + j*dil - pad_left][c]   (rows outside
+ *                  [0, x_rows) read as zero -- the reference's zero "same" padding)
+ *
+ * followed by one of the fused epilogues below.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  void*   ptr;      /* base of [utterance][row][channel]                                      */
+  int64_t bstride;  /* elements between utterances (0 = shared by all utterances)             */
+  int32_t ld;       /* elements between rows                                                  */
+  int32_t _pad;
+} qvc_tensor;
+
+typedef enum {
+  QVC_EPI_LINEAR = 0, /* per column segment: v = alpha*(acc+bias) [+ res]; w = [accin +] beta*v;
+                         raw <- w ; op <- round(leaky_relu(w, slope))                          */
+  QVC_EPI_GATE = 1,   /* WN gate (modules.py:14-34): cout = 2H; op[n] <- round(tanh(a[n]) *
+                         sigmoid(a[n+H])), a = acc + bias                                      */
+  QVC_EPI_SAMPLE = 2  /* prior sample (models.py:93-94): cout = 2H; z = a[n] + noise*exp(a[n+H]);
+                         raw <- z ; op <- round(z); optional m / logs copies                   */
+} qvc_epilogue;
+
+typedef struct {
+  int32_t    col0, ncols;   /* output columns [col0, col0+ncols) of the GEMM feed this segment;
+                               column n lands in channel n-col0 of the tensors below           */
+  float      alpha, beta;   /* see QVC_EPI_LINEAR                                              */
+  float      slope;         /* leaky-relu slope applied to the operand copy (1 = identity)     */
+  int32_t    _pad;
+  qvc_tensor res;           /* fp32, optional (ptr NULL = absent)                              */
+  qvc_tensor accin;         /* fp32, optional                                                  */
+  qvc_tensor raw;           /* fp32 out, optional                                              */
+  qvc_tensor op;            /* operand-format out, optional                                    */
+} qvc_epi_segment;
+
+typedef struct {
+  /* input series */
+  qvc_tensor x;             /* operand format                                                  */
+  int32_t    batch;         /* utterances                                                      */
+  int32_t    x_rows;        /* rows (frames) per utterance in x                                */
+  int32_t    out_rows;      /* rows produced per utterance                                     */
+  int32_t    cin;           /* multiple of 16                                                  */
+  /* filter */
+  const void*  w;           /* [cout][k][cin], operand format                                  */
+  const float* bias;        /* [cout] fp32, or per-utterance [batch][bias_bstride]; may be NULL */
+  int64_t    bias_bstride;  /* 0 = shared                                                      */
+  int32_t    cout;          /* GEMM columns (multiple of 16)                                   */
+  int32_t    k, dil, pad_left;
+  /* epilogue */
+  int32_t    epilogue;      /* qvc_epilogue                                                    */
+  int32_t    nseg;          /* QVC_EPI_LINEAR: 1 or 2 segments                                 */
+  qvc_epi_segment seg[2];   /* GATE / SAMPLE use seg[0].raw / seg[0].op with H = cout/2 channels */
+  qvc_tensor noise;         /* SAMPLE: fp32 [b][t][H]                                          */
+  qvc_tensor aux0, aux1;    /* SAMPLE: optional fp32 copies of m and logs                      */
+  int32_t    opformat;      /* qvc_opformat of x, w and every `op` output                      */
+  int32_t    backend;       /* qvc_backend                                                     */
+} qvc_conv_args;
+
+int qvc_conv1d(const qvc_conv_args* args, qvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / format helpers
+ * ------------------------------------------------------------------------------------------- */
+/* (B, C, T) fp32 -> [B][T][C] in `opformat` (rounded).  Replaces the implicit NCT layout of
+ * `unit` / noise at models.py:625,94. */
+int qvc_to_series_major(const float* src, void* dst, int batch, int channels, int frames,
+                        int opformat, qvc_stream_t stream);
+/* [B][T][ld>=C] fp32 -> (B, C, T) fp32 (debug taps). */
+int qvc_from_series_major(const float* src, int ld, float* dst, int batch, int channels, int frames,
+                          qvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Speaker encoder: SpeakerEncoder.embed_utterance / forward (models.py:507-546).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w_ih[3];   /* (1024, 80|256|256) row-major, gate rows i,f,g,o                  */
+  const float* w_hh[3];   /* (1024, 256)                                                       */
+  const float* bias[3];   /* (1024) = bias_ih + bias_hh, summed once at fold time              */
+  const float* lin_w;     /* (256, 256)                                                        */
+  const float* lin_b;     /* (256)                                                             */
+} qvc_spk_weights;
+
+/* mel (Bm, 80, Tm) fp32, reference layout.  Tm > 128 requires Bm == 1 and yields one embedding
+ * (mean over the 128-frame windows, hop 64, plus the last window); Tm <= 128 yields Bm embeddings.
+ * g_out :: [n_embed][256] fp32.  workspace: qvc_spk_workspace_bytes(). */
+size_t qvc_spk_workspace_bytes(int bm, int tm);
+int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm, int tm, float* g_out,
+                  void* workspace, size_t workspace_bytes, qvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tail: magnitude exp / phase pi*sin, 16-point inverse real DFT, Hann window, hop-4 overlap-add,
+ * envelope division and trim (torch.istft as called at models.py:350,399-401), then the x4
+ * zero-stuffing and the learnable 4->1 synthesis filter (models.py:404-406), fused.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* window;    /* (16) dec.stft.window                                              */
+  const float* synth;     /* [4 bands][4 phases][17 taps] folded from dec.updown_filter and
+                             dec.multistream_conv_post (see fold.py)                           */
+} qvc_tail_weights;
+
+/* post :: [B][frames][ld] fp32 with 72 live channels (band*18 + {0..8 log-mag, 9..17 phase});
+ * wave :: (B, 1, 16*(frames-1)) fp32; y_mb (optional) :: (B, 4, 4*(frames-1)) fp32. */
+int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, int batch, int frames,
+             float* wave, float* y_mb, qvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole path
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  w;          /* [cout][k][cin] operand format                                    */
+  const float* bias;       /* [cout] fp32 or NULL                                              */
+  int32_t cin, cout, k, dil, pad_left, _pad;
+} qvc_layer;
+
+/* Canonical layer order of qvc_model.layers (see qvc_layer_index_* below):
+ *   0            enc_p.pre                      (models.py:71)
+ *   1..16        enc_p.enc.in_layers.i          (modules.py:64)
+ *   17..32       enc_p.enc.res_skip_layers.i    (modules.py:67)
+ *   33           enc_p.proj                     (models.py:73)
+ *   34+10c ..    coupling c = 0..3 in EXECUTION order (flows 6,4,2,0; modules.py:193-195):
+ *                  +0 pre, +1..+4 in_layers, +5..+8 res_skip_layers, +9 post
+ *   74           dec.conv_pre                   (models.py:327)
+ *   75, 76       dec.ups.0, dec.ups.1 as polyphase series convolutions (models.py:333-335)
+ *   77+6r ..     dec.resblocks.r, r = 0..5: +0..+2 convs1.j, +3..+5 convs2.j (modules.py:133-144)
+ *   113          dec.subband_conv_post          (models.py:346)
+ */
+#define QVC_NUM_LAYERS 114
+
+typedef struct {
+  int32_t abi_version;      /* QVC_ABI_VERSION                                                  */
+  int32_t opformat;         /* qvc_opformat of every layer's w                                  */
+  int32_t backend;          /* qvc_backend                                                      */
+  int32_t chunk_utts;       /* decoder sub-batch (utterances) kept L2-resident; 0 = auto        */
+  qvc_layer layers[QVC_NUM_LAYERS];
+  /* speaker conditioning folded to per-utterance bias vectors:
+   * cond_w :: [cond_rows][256] fp32, cond_b :: [cond_rows] fp32 where the rows are
+   * 4 couplings x (4 layers x 384) gate biases (cond_layer + in_layer bias, modules.py:83-96)
+   * followed by 512 rows of dec.cond + dec.conv_pre bias (models.py:372). */
+  const float* cond_w;
+  const float* cond_b;
+  int32_t cond_rows;        /* 4*1536 + 512 = 6656                                              */
+  int32_t _pad;
+  qvc_spk_weights spk;
+  qvc_tail_weights tail;
+} qvc_model;
+
+/* Optional per-stage copies in the reference layout (B, C, T) fp32; NULL = skip.
+ * Names follow SURVEY.md section 8a. */
+typedef struct {
+  float* g;          /* (n_embed, 256)         */
+  float* m_p;        /* (B, 192, T)            */
+  float* logs_p;     /* (B, 192, T)            */
+  float* z_p;        /* (B, 192, T)            */
+  float* flow[4];    /* after couplings 6,4,2,0 (B, 192, T), reference channel order */
+  float* conv_pre;   /* (B, 512, T)            */
+  float* ups0;       /* (B, 256, 5T)           */
+  float* mrf0;       /* (B, 256, 5T)           */
+  float* ups1;       /* (B, 128, 20T)          */
+  float* mrf1;       /* (B, 128, 20T)          */
+  float* conv_post;  /* (B, 72, 20T+1)         */
+  float* y_mb;       /* (B, 4, 80T)            */
+} qvc_taps;
+
+size_t qvc_infer_workspace_bytes(const qvc_model* model, int batch, int frames, int mel_batch,
+                                 int mel_frames);
+
+/* unit (B,256,T), mel (Bm,80,Tm), noise (B,192,T) [the torch.randn_like draw of models.py:94],
+ * wave (B,1,320T); all fp32 device pointers in the reference layout.
+ * g_in (optional, [n_embed][256]): a cached speaker embedding; when non-NULL the speaker encoder
+ * is skipped and mel may be NULL. */
+int qvc_infer(const qvc_model* model, const float* unit, const float* mel, const float* noise,
+              const float* g_in, int batch, int frames, int mel_batch, int mel_frames,
+              float* wave, const qvc_taps* taps, void* workspace, size_t workspace_bytes,
+              qvc_stream_t stream);
+
+/* Decoder only (BASELINE.json config 3): z (B,192,T) fp32, g [1|B][256] fp32. */
+int qvc_decode(const qvc_model* model, const float* z, const float* g, int g_batch, int batch,
+               int frames, float* wave, const qvc_taps* taps, void* workspace,
+               size_t workspace_bytes, qvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Misc
+ * ------------------------------------------------------------------------------------------- */
+const char* qvc_last_error(void);
+int qvc_abi_version(void);
+/* number of kernel launches enqueued by this process through the library (all streams). */
+uint64_t qvc_launch_count(void);
+/* 0 when device `dev` is an sm_100 part this library has code for. */
+int qvc_check_device(int dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QVC_B200_H_ */

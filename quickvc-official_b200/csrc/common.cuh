@@ -1,0 +1,270 @@
+// common.cuh -- shared device/host helpers for libqvc_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/qvc_b200.h"
+
+namespace qvc {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define QVC_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::qvc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return QVC_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define QVC_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::qvc::set_error(__VA_ARGS__);           \
+      return QVC_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+
+#define QVC_PROPAGATE(expr)      \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != QVC_OK) return _s; \
+  } while (0)
+
+inline int post_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return QVC_ERR_CUDA;
+  }
+  count_launch();
+  return QVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand formats
+// ---------------------------------------------------------------------------------------------
+template <int OPF> struct OpType;
+template <> struct OpType<QVC_OPF_F32>  { using type = float; };
+template <> struct OpType<QVC_OPF_TF32> { using type = float; };
+template <> struct OpType<QVC_OPF_BF16> { using type = __nv_bfloat16; };
+
+inline size_t opformat_bytes(int opf) { return opf == QVC_OPF_BF16 ? 2 : 4; }
+
+__device__ __forceinline__ float round_tf32(float v) {
+  // round-to-nearest (ties away) to the 10-bit-mantissa TF32 grid; stays an fp32 bit pattern
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+template <int OPF> __device__ __forceinline__ typename OpType<OPF>::type to_operand(float v);
+template <> __device__ __forceinline__ float to_operand<QVC_OPF_F32>(float v) { return v; }
+template <> __device__ __forceinline__ float to_operand<QVC_OPF_TF32>(float v) { return round_tf32(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_operand<QVC_OPF_BF16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float op_to_float(float v) { return v; }
+__device__ __forceinline__ float op_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
+
+// ---------------------------------------------------------------------------------------------
+// device view of qvc_tensor / epilogue description (POD, passed by value to kernels)
+// ---------------------------------------------------------------------------------------------
+struct TRef {
+  void*   ptr;
+  int64_t bs;
+  int32_t ld;
+  __device__ __forceinline__ bool present() const { return ptr != nullptr; }
+  template <typename T>
+  __device__ __forceinline__ T* at(int b, int row, int col) const {
+    return reinterpret_cast<T*>(ptr) + (int64_t)b * bs + (int64_t)row * ld + col;
+  }
+};
+
+struct EpiSeg {
+  int32_t col0, ncols;
+  float alpha, beta, slope;
+  TRef res, accin, raw, op;
+};
+
+struct EpiParams {
+  int32_t mode;       // qvc_epilogue
+  int32_t nseg;
+  int32_t half;       // H for GATE / SAMPLE
+  int32_t out_rows;
+  const float* bias;
+  int64_t bias_bs;
+  EpiSeg seg[2];
+  TRef noise, aux0, aux1;
+};
+
+inline TRef make_tref(const qvc_tensor& t) { return TRef{t.ptr, t.bstride, t.ld}; }
+
+// Store VEC consecutive operand values.
+template <int OPF, int VEC>
+__device__ __forceinline__ void store_operand(typename OpType<OPF>::type* dst, const float* v) {
+  if constexpr (OPF == QVC_OPF_BF16) {
+    if constexpr (VEC == 2) {
+      *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v[0], v[1]);
+    } else if constexpr (VEC == 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst) = u;
+    } else {
+      static_assert(VEC == 8, "VEC");
+      uint4 u;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
+      __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      u.z = *reinterpret_cast<uint32_t*>(&c);
+      u.w = *reinterpret_cast<uint32_t*>(&d);
+      *reinterpret_cast<uint4*>(dst) = u;
+    }
+  } else {
+    float r[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r[i] = to_operand<OPF>(v[i]);
+    if constexpr (VEC == 2) {
+      *reinterpret_cast<float2*>(dst) = make_float2(r[0], r[1]);
+    } else if constexpr (VEC == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+      static_assert(VEC == 8, "VEC");
+      reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_f32(const float* src, float* v) {
+  if constexpr (VEC == 2) {
+    float2 t = *reinterpret_cast<const float2*>(src);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      float4 t = *reinterpret_cast<const float4*>(src + i);
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_f32(float* dst, const float* v) {
+  if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4)
+      *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared epilogues.  `acc` holds VEC consecutive GEMM columns starting at column n (n % VEC == 0)
+// of output row (b, t).  Used by both the FMA and the tcgen05 convolution kernels so that the two
+// back ends differ only in how the accumulator was produced.
+// ---------------------------------------------------------------------------------------------
+template <int OPF, int VEC>
+__device__ __forceinline__ void epi_linear(const EpiParams& ep, int b, int t, int n, const float* acc) {
+  using OT = typename OpType<OPF>::type;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (s >= ep.nseg) break;
+    const EpiSeg& sg = ep.seg[s];
+    if (n < sg.col0 || n >= sg.col0 + sg.ncols) continue;
+    const int c = n - sg.col0;
+    float v[VEC];
+    const float* bias = ep.bias ? ep.bias + (int64_t)b * ep.bias_bs + n : nullptr;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = sg.alpha * (acc[i] + (bias ? bias[i] : 0.f));
+    if (sg.res.present()) {
+      float r[VEC];
+      load_f32<VEC>(sg.res.at<float>(b, t, c), r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] += r[i];
+    }
+    if (sg.accin.present()) {
+      float r[VEC];
+      load_f32<VEC>(sg.accin.at<float>(b, t, c), r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = r[i] + sg.beta * v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = sg.beta * v[i];
+    }
+    if (sg.raw.present()) store_f32<VEC>(sg.raw.at<float>(b, t, c), v);
+    if (sg.op.present()) {
+      float a[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) a[i] = leaky(v[i], sg.slope);
+      store_operand<OPF, VEC>(sg.op.at<OT>(b, t, c), a);
+    }
+  }
+}
+
+// lo = columns [n, n+VEC) of the first half, hi = the matching columns of the second half.
+template <int OPF, int VEC>
+__device__ __forceinline__ void epi_gate(const EpiParams& ep, int b, int t, int n, const float* lo,
+                                         const float* hi) {
+  using OT = typename OpType<OPF>::type;
+  const float* bias = ep.bias + (int64_t)b * ep.bias_bs;
+  float a[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float ta = lo[i] + bias[n + i];
+    float sa = hi[i] + bias[ep.half + n + i];
+    a[i] = tanhf(ta) * sigmoid_acc(sa);
+  }
+  const EpiSeg& sg = ep.seg[0];
+  if (sg.raw.present()) store_f32<VEC>(sg.raw.at<float>(b, t, n), a);
+  if (sg.op.present()) store_operand<OPF, VEC>(sg.op.at<OT>(b, t, n), a);
+}
+
+template <int OPF, int VEC>
+__device__ __forceinline__ void epi_sample(const EpiParams& ep, int b, int t, int n, const float* lo,
+                                           const float* hi) {
+  using OT = typename OpType<OPF>::type;
+  const float* bias = ep.bias + (int64_t)b * ep.bias_bs;
+  float m[VEC], lg[VEC], z[VEC], nz[VEC];
+  load_f32<VEC>(ep.noise.at<float>(b, t, n), nz);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    m[i] = lo[i] + bias[n + i];
+    lg[i] = hi[i] + bias[ep.half + n + i];
+    z[i] = m[i] + nz[i] * expf(lg[i]);
+  }
+  const EpiSeg& sg = ep.seg[0];
+  if (ep.aux0.present()) store_f32<VEC>(ep.aux0.at<float>(b, t, n), m);
+  if (ep.aux1.present()) store_f32<VEC>(ep.aux1.at<float>(b, t, n), lg);
+  if (sg.raw.present()) store_f32<VEC>(sg.raw.at<float>(b, t, n), z);
+  if (sg.op.present()) store_operand<OPF, VEC>(sg.op.at<OT>(b, t, n), z);
+}
+
+// host-side translation of the public argument struct
+int build_epi_params(const qvc_conv_args& a, EpiParams* ep);
+
+// kernels' host launchers (defined in the respective .cu files)
+int launch_conv_fma(const qvc_conv_args& a, cudaStream_t stream);
+int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream);
+
+}  // namespace qvc

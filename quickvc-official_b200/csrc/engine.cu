@@ -1,0 +1,417 @@
+// engine.cu -- enqueues SynthesizerTrn.infer (models.py:625-642) as a fixed sequence of series
+// convolutions with fused epilogues, the persistent-RNN speaker encoder and the fused tail.
+//
+// Data layout in HBM (all "series-major" [utterance][frame][channel]):
+//   *R buffers: fp32 residual / skip streams (never rounded)
+//   *O buffers: GEMM operands in the model's operand format (TF32-rounded fp32, or bf16), with the
+//               next layer's leaky-relu already applied by the producing epilogue
+// Whole-batch buffers serve the prior encoder and the flow (192 channels at the unit frame rate);
+// the decoder runs per sub-batch of `chunk_utts` utterances so that its working set (the 256- and
+// 128-channel series at 5x / 20x the frame rate) stays resident in the 126 MB L2.
+#include "common.cuh"
+#include "engine.h"
+
+namespace qvc {
+
+namespace {
+
+constexpr int HID = 192;        // inter / hidden channels (configs/quickvc.json:41-42)
+constexpr int UNIT_CH = 256;    // models.py:579
+constexpr int GIN = 256;
+constexpr int C_PRE = 512, C_UP0 = 256, C_UP1 = 128, C_POST = 72;
+constexpr int UP0 = 5, UP1 = 4;
+
+// canonical layer order (qvc_b200.h)
+constexpr int L_ENC_PRE = 0, L_ENC_IN = 1, L_ENC_RS = 17, L_ENC_PROJ = 33, L_FLOW = 34, L_DEC_PRE = 74,
+              L_UPS = 75, L_RES = 77, L_POST = 113;
+
+struct Bump {
+  char* base; size_t off = 0, cap;
+  Bump(void* b, size_t c) : base(reinterpret_cast<char*>(b)), cap(c) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  }
+};
+
+struct Shapes { int B, T, n_embed; int cb; };
+
+struct Buffers {
+  // whole batch
+  void *unitO, *xO, *actsO, *skipO, *zO;
+  float *noiseT, *xR, *skipR, *zR, *tapA, *tapB, *condvec, *g;
+  void* spk_ws; size_t spk_ws_bytes;
+  // per decoder sub-batch
+  void *aO, *x1O, *t1O, *xaO, *uO, *y1O, *t2O, *yaO, *pO;
+  float *x1R, *xaR, *sum1R, *y1R, *yaR, *sum2R, *cpR;
+};
+
+int pick_chunk(const qvc_model* m, int B, int T) {
+  int cb = m->chunk_utts;
+  if (cb <= 0) {
+    // five live 128-channel fp32 series at 20x the frame rate per utterance; aim for ~64 MB
+    const double per_utt = 5.0 * 20.0 * T * C_UP1 * 4.0;
+    cb = (int)(64.0 * 1024 * 1024 / (per_utt > 1 ? per_utt : 1));
+    if (cb < 1) cb = 1;
+  }
+  return cb > B ? B : cb;
+}
+
+size_t carve(const qvc_model* m, const Shapes& s, int mel_batch, int mel_frames, bool with_spk,
+             void* ws, size_t cap, Buffers* b) {
+  Bump a(ws, cap);
+  const size_t E = opformat_bytes(m->opformat);
+  const size_t n1 = (size_t)s.B * s.T;
+  b->unitO = a.take(n1 * UNIT_CH * E);
+  b->noiseT = (float*)a.take(n1 * HID * 4);
+  b->xR = (float*)a.take(n1 * HID * 4);      b->xO = a.take(n1 * HID * E);
+  b->actsO = a.take(n1 * HID * E);
+  b->skipR = (float*)a.take(n1 * HID * 4);   b->skipO = a.take(n1 * HID * E);
+  b->zR = (float*)a.take(n1 * HID * 4);      b->zO = a.take(n1 * HID * E);
+  b->tapA = (float*)a.take(n1 * HID * 4);    b->tapB = (float*)a.take(n1 * HID * 4);
+  b->condvec = (float*)a.take((size_t)s.n_embed * m->cond_rows * 4);
+  b->g = (float*)a.take((size_t)s.n_embed * GIN * 4);
+  b->spk_ws_bytes = with_spk ? qvc_spk_workspace_bytes(mel_batch, mel_frames) : 0;
+  b->spk_ws = a.take(b->spk_ws_bytes);
+  const size_t c = (size_t)s.cb, T = (size_t)s.T;
+  const size_t r0 = c * UP0 * T, r1 = c * UP0 * UP1 * T, rp = c * (UP0 * UP1 * T + 1);
+  b->aO = a.take(c * T * C_PRE * E);
+  b->x1R = (float*)a.take(r0 * C_UP0 * 4);   b->x1O = a.take(r0 * C_UP0 * E);
+  b->t1O = a.take(r0 * C_UP0 * E);
+  b->xaR = (float*)a.take(r0 * C_UP0 * 4);   b->xaO = a.take(r0 * C_UP0 * E);
+  b->sum1R = (float*)a.take(r0 * C_UP0 * 4); b->uO = a.take(r0 * C_UP0 * E);
+  b->y1R = (float*)a.take(r1 * C_UP1 * 4);   b->y1O = a.take(r1 * C_UP1 * E);
+  b->t2O = a.take(r1 * C_UP1 * E);
+  b->yaR = (float*)a.take(r1 * C_UP1 * 4);   b->yaO = a.take(r1 * C_UP1 * E);
+  b->sum2R = (float*)a.take(r1 * C_UP1 * 4);
+  b->pO = a.take(rp * C_UP1 * E);
+  b->cpR = (float*)a.take(rp * C_POST * 4);
+  return a.off;
+}
+
+struct Ctx {
+  const qvc_model* m;
+  cudaStream_t st;
+  size_t E;
+};
+
+inline qvc_tensor tens(const void* p, int64_t bs, int ld) { return qvc_tensor{const_cast<void*>(p), bs, ld, 0}; }
+inline qvc_tensor none() { return qvc_tensor{nullptr, 0, 0, 0}; }
+
+inline qvc_epi_segment seg(int col0, int ncols) {
+  qvc_epi_segment s{};
+  s.col0 = col0; s.ncols = ncols; s.alpha = 1.f; s.beta = 1.f; s.slope = 1.f;
+  return s;
+}
+
+qvc_conv_args layer_args(const Ctx& c, int li, qvc_tensor x, int batch, int x_rows, int out_rows) {
+  const qvc_layer& L = c.m->layers[li];
+  qvc_conv_args a{};
+  a.x = x; a.batch = batch; a.x_rows = x_rows; a.out_rows = out_rows;
+  a.cin = L.cin; a.w = L.w; a.bias = L.bias; a.bias_bstride = 0;
+  a.cout = L.cout; a.k = L.k; a.dil = L.dil; a.pad_left = L.pad_left;
+  a.epilogue = QVC_EPI_LINEAR; a.nseg = 1;
+  a.opformat = c.m->opformat; a.backend = c.m->backend;
+  return a;
+}
+
+int run(const Ctx& c, const qvc_conv_args& a) { return qvc_conv1d(&a, (qvc_stream_t)c.st); }
+
+// One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack
+// input; on return skipO holds the operand copy of the summed skip output.
+int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, int n_layers,
+           const float* gate_bias, int64_t gate_bias_bs, int gate_bias_layer_stride) {
+  const int64_t bs = (int64_t)T * HID;
+  for (int i = 0; i < n_layers; ++i) {
+    qvc_conv_args a = layer_args(c, l_in + i, tens(bf.xO, bs, HID), B, T, T);
+    a.epilogue = QVC_EPI_GATE;
+    if (gate_bias) { a.bias = gate_bias + (int64_t)i * gate_bias_layer_stride; a.bias_bstride = gate_bias_bs; }
+    a.seg[0] = seg(0, HID);
+    a.seg[0].op = tens(bf.actsO, bs, HID);
+    QVC_PROPAGATE(run(c, a));
+
+    qvc_conv_args r = layer_args(c, l_rs + i, tens(bf.actsO, bs, HID), B, T, T);
+    if (i < n_layers - 1) {
+      r.nseg = 2;
+      r.seg[0] = seg(0, HID);                       // residual half: x += ...
+      r.seg[0].res = tens(bf.xR, bs, HID);
+      r.seg[0].raw = tens(bf.xR, bs, HID);
+      r.seg[0].op = tens(bf.xO, bs, HID);
+      r.seg[1] = seg(HID, HID);                     // skip half: out += ...
+      if (i > 0) r.seg[1].accin = tens(bf.skipR, bs, HID);
+      r.seg[1].raw = tens(bf.skipR, bs, HID);
+    } else {
+      r.nseg = 1;                                   // last layer: skip only (modules.py:110-112)
+      r.seg[0] = seg(0, HID);
+      if (i > 0) r.seg[0].accin = tens(bf.skipR, bs, HID);
+      r.seg[0].op = tens(bf.skipO, bs, HID);
+    }
+    QVC_PROPAGATE(run(c, r));
+  }
+  return QVC_OK;
+}
+
+// MRF = mean of three ResBlock1 (models.py:378-384, modules.py:147-154) on a sub-batch.
+int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void* x1O, void* tO,
+            float* xaR, void* xaO, float* sumR, qvc_tensor final_op, float final_slope, float* final_raw) {
+  const int64_t bs = (int64_t)rows * ch;
+  for (int r = 0; r < 3; ++r) {
+    const int lb = l_res0 + 6 * r;
+    const float* srcR = x1R;
+    const void* srcO = x1O;
+    for (int j = 0; j < 3; ++j) {
+      qvc_conv_args a = layer_args(c, lb + j, tens(srcO, bs, ch), cb, rows, rows);
+      a.seg[0] = seg(0, ch);
+      a.seg[0].slope = 0.1f;
+      a.seg[0].op = tens(tO, bs, ch);
+      QVC_PROPAGATE(run(c, a));
+
+      qvc_conv_args d = layer_args(c, lb + 3 + j, tens(tO, bs, ch), cb, rows, rows);
+      d.seg[0] = seg(0, ch);
+      d.seg[0].res = tens(srcR, bs, ch);
+      if (j < 2) {
+        d.seg[0].raw = tens(xaR, bs, ch);
+        d.seg[0].op = tens(xaO, bs, ch);
+        d.seg[0].slope = 0.1f;
+        srcR = xaR; srcO = xaO;
+      } else {
+        d.seg[0].beta = 1.f / 3.f;
+        if (r > 0) d.seg[0].accin = tens(sumR, bs, ch);
+        if (r < 2) {
+          d.seg[0].raw = tens(sumR, bs, ch);
+        } else {
+          d.seg[0].op = final_op;
+          d.seg[0].slope = final_slope;
+          if (final_raw) d.seg[0].raw = tens(final_raw, bs, ch);
+        }
+      }
+      QVC_PROPAGATE(run(c, d));
+    }
+  }
+  return QVC_OK;
+}
+
+// Multistream_iSTFT_Generator.forward (models.py:360-408) on the whole batch, sub-batch by sub-batch.
+int run_decoder(const Ctx& c, const Buffers& bf, const Shapes& s, const void* zO, const float* condvec,
+                float* wave, const qvc_taps* taps) {
+  const int T = s.T, R0 = UP0 * T, R1 = UP0 * UP1 * T, RP = R1 + 1;
+  const size_t E = c.E;
+  for (int b0 = 0; b0 < s.B; b0 += s.cb) {
+    const int cb = (s.B - b0 < s.cb) ? s.B - b0 : s.cb;
+    const char* zO_b = reinterpret_cast<const char*>(zO) + (size_t)b0 * T * HID * E;
+    // conv_pre + cond(g): the conditioning is a per-utterance bias (models.py:372)
+    {
+      qvc_conv_args a = layer_args(c, L_DEC_PRE, tens(zO_b, (int64_t)T * HID, HID), cb, T, T);
+      a.bias = condvec + (c.m->cond_rows - C_PRE) + (s.n_embed > 1 ? (int64_t)b0 * c.m->cond_rows : 0);
+      a.bias_bstride = s.n_embed > 1 ? c.m->cond_rows : 0;
+      a.seg[0] = seg(0, C_PRE);
+      a.seg[0].slope = 0.1f;
+      a.seg[0].op = tens(bf.aO, (int64_t)T * C_PRE, C_PRE);
+      if (taps && taps->conv_pre) a.seg[0].raw = tens(bf.x1R, (int64_t)T * C_PRE, C_PRE);
+      QVC_PROPAGATE(run(c, a));
+      if (taps && taps->conv_pre)
+        QVC_PROPAGATE(from_series_major(bf.x1R, C_PRE, (int64_t)T * C_PRE, taps->conv_pre + (size_t)b0 * C_PRE * T,
+                                        cb, C_PRE, T, false, c.st));
+    }
+    // ups.0 as a 4-tap series convolution with 5*256 phase-major output columns: [T][1280] == [5T][256]
+    {
+      qvc_conv_args a = layer_args(c, L_UPS + 0, tens(bf.aO, (int64_t)T * C_PRE, C_PRE), cb, T, T);
+      a.seg[0] = seg(0, UP0 * C_UP0);
+      a.seg[0].slope = 0.1f;
+      a.seg[0].raw = tens(bf.x1R, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
+      a.seg[0].op = tens(bf.x1O, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
+      QVC_PROPAGATE(run(c, a));
+      if (taps && taps->ups0)
+        QVC_PROPAGATE(from_series_major(bf.x1R, C_UP0, (int64_t)R0 * C_UP0, taps->ups0 + (size_t)b0 * C_UP0 * R0,
+                                        cb, C_UP0, R0, false, c.st));
+    }
+    {
+      const bool tap = taps && taps->mrf0;
+      QVC_PROPAGATE(run_mrf(c, cb, R0, C_UP0, L_RES, bf.x1R, bf.x1O, bf.t1O, bf.xaR, bf.xaO, bf.sum1R,
+                            tens(bf.uO, (int64_t)R0 * C_UP0, C_UP0), 0.1f, tap ? bf.xaR : nullptr));
+      if (tap)
+        QVC_PROPAGATE(from_series_major(bf.xaR, C_UP0, (int64_t)R0 * C_UP0, taps->mrf0 + (size_t)b0 * C_UP0 * R0,
+                                        cb, C_UP0, R0, false, c.st));
+    }
+    // ups.1: 5 taps, 4*128 phase-major columns: [5T][512] == [20T][128]
+    {
+      qvc_conv_args a = layer_args(c, L_UPS + 1, tens(bf.uO, (int64_t)R0 * C_UP0, C_UP0), cb, R0, R0);
+      a.seg[0] = seg(0, UP1 * C_UP1);
+      a.seg[0].slope = 0.1f;
+      a.seg[0].raw = tens(bf.y1R, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
+      a.seg[0].op = tens(bf.y1O, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
+      QVC_PROPAGATE(run(c, a));
+      if (taps && taps->ups1)
+        QVC_PROPAGATE(from_series_major(bf.y1R, C_UP1, (int64_t)R1 * C_UP1, taps->ups1 + (size_t)b0 * C_UP1 * R1,
+                                        cb, C_UP1, R1, false, c.st));
+    }
+    {
+      // final operand: leaky_relu with the DEFAULT slope 0.01 (models.py:385), written one row
+      // down into the reflection-padded series (models.py:388)
+      const bool tap = taps && taps->mrf1;
+      qvc_tensor fo = tens(reinterpret_cast<char*>(bf.pO) + (size_t)C_UP1 * E, (int64_t)RP * C_UP1, C_UP1);
+      QVC_PROPAGATE(run_mrf(c, cb, R1, C_UP1, L_RES + 18, bf.y1R, bf.y1O, bf.t2O, bf.yaR, bf.yaO, bf.sum2R,
+                            fo, 0.01f, tap ? bf.yaR : nullptr));
+      if (tap)
+        QVC_PROPAGATE(from_series_major(bf.yaR, C_UP1, (int64_t)R1 * C_UP1, taps->mrf1 + (size_t)b0 * C_UP1 * R1,
+                                        cb, C_UP1, R1, false, c.st));
+      QVC_PROPAGATE(reflect_row(bf.pO, (int64_t)RP * C_UP1 * E, (int)(C_UP1 * E), cb, c.st));
+    }
+    {
+      qvc_conv_args a = layer_args(c, L_POST, tens(bf.pO, (int64_t)RP * C_UP1, C_UP1), cb, RP, RP);
+      a.seg[0] = seg(0, C_POST);
+      a.seg[0].raw = tens(bf.cpR, (int64_t)RP * C_POST, C_POST);
+      QVC_PROPAGATE(run(c, a));
+      if (taps && taps->conv_post)
+        QVC_PROPAGATE(from_series_major(bf.cpR, C_POST, (int64_t)RP * C_POST, taps->conv_post + (size_t)b0 * C_POST * RP,
+                                        cb, C_POST, RP, false, c.st));
+    }
+    QVC_PROPAGATE(qvc_tail(&c.m->tail, bf.cpR, C_POST, cb, RP, wave + (size_t)b0 * 16 * R1,
+                           (taps && taps->y_mb) ? taps->y_mb + (size_t)b0 * 4 * 4 * R1 : nullptr,
+                           (qvc_stream_t)c.st));
+  }
+  return QVC_OK;
+}
+
+int check_model(const qvc_model* m) {
+  QVC_REQUIRE(m != nullptr, "null model");
+  QVC_REQUIRE(m->abi_version == QVC_ABI_VERSION, "model built for ABI %d, library is %d", m->abi_version, QVC_ABI_VERSION);
+  QVC_REQUIRE(m->opformat >= QVC_OPF_F32 && m->opformat <= QVC_OPF_BF16, "bad opformat %d", m->opformat);
+  QVC_REQUIRE(m->backend == QVC_BACKEND_FMA || m->backend == QVC_BACKEND_TCGEN05, "bad backend %d", m->backend);
+  QVC_REQUIRE(!(m->backend == QVC_BACKEND_TCGEN05 && m->opformat == QVC_OPF_F32),
+              "the tcgen05 back end needs TF32 or BF16 operands");
+  QVC_REQUIRE(m->cond_rows == 4 * 4 * 2 * HID + C_PRE, "cond_rows %d != %d", m->cond_rows, 4 * 4 * 2 * HID + C_PRE);
+  for (int i = 0; i < QVC_NUM_LAYERS; ++i)
+    QVC_REQUIRE(m->layers[i].w != nullptr && m->layers[i].cin > 0 && m->layers[i].cout > 0, "layer %d not populated", i);
+  QVC_REQUIRE(m->cond_w && m->cond_b && m->tail.window && m->tail.synth, "model misses cond / tail weights");
+  return QVC_OK;
+}
+
+}  // namespace
+
+}  // namespace qvc
+
+using namespace qvc;
+
+extern "C" size_t qvc_infer_workspace_bytes(const qvc_model* m, int batch, int frames, int mel_batch, int mel_frames) {
+  if (!m || batch <= 0 || frames <= 0) return 0;
+  Shapes s{batch, frames, batch, pick_chunk(m, batch, frames)};   // n_embed upper bound = batch
+  Buffers b;
+  return carve(m, s, mel_batch, mel_frames, mel_batch > 0 && mel_frames > 0, nullptr, 0, &b) + 256;
+}
+
+extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel, const float* noise,
+                         const float* g_in, int batch, int frames, int mel_batch, int mel_frames,
+                         float* wave, const qvc_taps* taps, void* workspace, size_t workspace_bytes,
+                         qvc_stream_t stream) {
+  QVC_PROPAGATE(check_model(m));
+  QVC_REQUIRE(unit && noise && wave && workspace, "qvc_infer: null pointer");
+  QVC_REQUIRE(batch >= 1 && batch <= 65535 && frames >= 1, "qvc_infer: bad shape B=%d T=%d", batch, frames);
+  QVC_REQUIRE(g_in || mel, "qvc_infer: need mel or a cached embedding");
+  QVC_REQUIRE(mel_batch >= 1, "qvc_infer: mel_batch must be >= 1");
+  const bool with_spk = g_in == nullptr;
+  if (with_spk) {
+    QVC_REQUIRE(mel_frames >= 1, "qvc_infer: empty mel");
+    QVC_REQUIRE(mel_frames <= 128 || mel_batch == 1,
+                "qvc_infer: mel longer than 128 frames must have batch 1 (got %d), as in the reference (models.py:536)", mel_batch);
+  }
+  const int n_embed = with_spk ? (mel_frames > 128 ? 1 : mel_batch) : mel_batch;
+  QVC_REQUIRE(n_embed == 1 || n_embed == batch, "qvc_infer: %d embeddings cannot broadcast over %d utterances", n_embed, batch);
+
+  Shapes s{batch, frames, n_embed, pick_chunk(m, batch, frames)};
+  Buffers bf;
+  const uintptr_t mis = (uintptr_t)workspace & 255;
+  char* ws = reinterpret_cast<char*>(workspace) + (mis ? 256 - mis : 0);
+  const size_t cap = workspace_bytes - (mis ? 256 - mis : 0);
+  const size_t need = carve(m, s, mel_batch, mel_frames, with_spk, ws, cap, &bf);
+  if (need > cap) {
+    set_error("qvc_infer: workspace %zu < %zu", workspace_bytes, need + 256);
+    return QVC_ERR_WORKSPACE;
+  }
+  Ctx c{m, (cudaStream_t)stream, opformat_bytes(m->opformat)};
+  const int B = batch, T = frames;
+  const int64_t bs = (int64_t)T * HID;
+
+  // inputs -> series-major
+  QVC_PROPAGATE(qvc_to_series_major(unit, bf.unitO, B, UNIT_CH, T, m->opformat, stream));
+  QVC_PROPAGATE(qvc_to_series_major(noise, bf.noiseT, B, HID, T, QVC_OPF_F32, stream));
+
+  // speaker embedding and the per-utterance bias vectors derived from it (models.py:635)
+  const float* g = g_in;
+  if (with_spk) {
+    QVC_PROPAGATE(qvc_spk_embed(&m->spk, mel, mel_batch, mel_frames, bf.g, bf.spk_ws, bf.spk_ws_bytes, stream));
+    g = bf.g;
+  }
+  if (taps && taps->g)
+    QVC_CHECK_CUDA(cudaMemcpyAsync(taps->g, g, (size_t)n_embed * GIN * 4, cudaMemcpyDeviceToDevice, c.st));
+  QVC_PROPAGATE(cond_vectors(m->cond_w, m->cond_b, g, n_embed, m->cond_rows, bf.condvec, c.st));
+  const int64_t cond_bs = n_embed > 1 ? m->cond_rows : 0;
+
+  // prior encoder enc_p (models.py:75-95)
+  {
+    qvc_conv_args a = layer_args(c, L_ENC_PRE, tens(bf.unitO, (int64_t)T * UNIT_CH, UNIT_CH), B, T, T);
+    a.seg[0] = seg(0, HID);
+    a.seg[0].raw = tens(bf.xR, bs, HID);
+    a.seg[0].op = tens(bf.xO, bs, HID);
+    QVC_PROPAGATE(run(c, a));
+    QVC_PROPAGATE(run_wn(c, bf, B, T, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0));
+    qvc_conv_args p = layer_args(c, L_ENC_PROJ, tens(bf.skipO, bs, HID), B, T, T);
+    p.epilogue = QVC_EPI_SAMPLE;
+    p.noise = tens(bf.noiseT, bs, HID);
+    p.seg[0] = seg(0, HID);
+    p.seg[0].raw = tens(bf.zR, bs, HID);
+    p.seg[0].op = tens(bf.zO, bs, HID);
+    if (taps && taps->m_p) p.aux0 = tens(bf.tapA, bs, HID);
+    if (taps && taps->logs_p) p.aux1 = tens(bf.tapB, bs, HID);
+    QVC_PROPAGATE(run(c, p));
+    if (taps && taps->m_p) QVC_PROPAGATE(from_series_major(bf.tapA, HID, bs, taps->m_p, B, HID, T, false, c.st));
+    if (taps && taps->logs_p) QVC_PROPAGATE(from_series_major(bf.tapB, HID, bs, taps->logs_p, B, HID, T, false, c.st));
+    if (taps && taps->z_p) QVC_PROPAGATE(from_series_major(bf.zR, HID, bs, taps->z_p, B, HID, T, false, c.st));
+  }
+
+  // flow, reverse direction, Flips folded into the weights (models.py:39-51, modules.py:165-224)
+  for (int cpl = 0; cpl < 4; ++cpl) {
+    const int lb = L_FLOW + 10 * cpl;
+    qvc_conv_args a = layer_args(c, lb, tens(bf.zO, bs, HID), B, T, T);
+    a.seg[0] = seg(0, HID);
+    a.seg[0].raw = tens(bf.xR, bs, HID);
+    a.seg[0].op = tens(bf.xO, bs, HID);
+    QVC_PROPAGATE(run(c, a));
+    QVC_PROPAGATE(run_wn(c, bf, B, T, lb + 1, lb + 5, 4, bf.condvec + cpl * 4 * 2 * HID, cond_bs, 2 * HID));
+    qvc_conv_args p = layer_args(c, lb + 9, tens(bf.skipO, bs, HID), B, T, T);
+    p.seg[0] = seg(0, HID);
+    p.seg[0].alpha = -1.f;                          // x1 - m (modules.py:217)
+    p.seg[0].res = tens(bf.zR, bs, HID);
+    p.seg[0].raw = tens(bf.zR, bs, HID);
+    p.seg[0].op = tens(bf.zO, bs, HID);
+    QVC_PROPAGATE(run(c, p));
+    if (taps && taps->flow[cpl])
+      QVC_PROPAGATE(from_series_major(bf.zR, HID, bs, taps->flow[cpl], B, HID, T, (cpl & 1) == 0, c.st));
+  }
+
+  return run_decoder(c, bf, s, bf.zO, bf.condvec, wave, taps);
+}
+
+extern "C" int qvc_decode(const qvc_model* m, const float* z, const float* g, int g_batch, int batch,
+                          int frames, float* wave, const qvc_taps* taps, void* workspace,
+                          size_t workspace_bytes, qvc_stream_t stream) {
+  QVC_PROPAGATE(check_model(m));
+  QVC_REQUIRE(z && g && wave && workspace, "qvc_decode: null pointer");
+  QVC_REQUIRE(batch >= 1 && batch <= 65535 && frames >= 1, "qvc_decode: bad shape B=%d T=%d", batch, frames);
+  QVC_REQUIRE(g_batch == 1 || g_batch == batch, "qvc_decode: %d embeddings cannot broadcast over %d utterances", g_batch, batch);
+  Shapes s{batch, frames, g_batch, pick_chunk(m, batch, frames)};
+  Buffers bf;
+  const uintptr_t mis = (uintptr_t)workspace & 255;
+  char* ws = reinterpret_cast<char*>(workspace) + (mis ? 256 - mis : 0);
+  const size_t cap = workspace_bytes - (mis ? 256 - mis : 0);
+  const size_t need = carve(m, s, 0, 0, false, ws, cap, &bf);
+  if (need > cap) {
+    set_error("qvc_decode: workspace %zu < %zu", workspace_bytes, need + 256);
+    return QVC_ERR_WORKSPACE;
+  }
+  Ctx c{m, (cudaStream_t)stream, opformat_bytes(m->opformat)};
+  QVC_PROPAGATE(qvc_to_series_major(z, bf.zO, batch, HID, frames, m->opformat, stream));
+  QVC_PROPAGATE(cond_vectors(m->cond_w, m->cond_b, g, g_batch, m->cond_rows, bf.condvec, c.st));
+  return run_decoder(c, bf, s, bf.zO, bf.condvec, wave, taps);
+}

@@ -1,0 +1,14 @@
+// engine.h -- internal helpers shared by the translation units of libqvc_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qvc {
+
+int from_series_major(const float* src, int ld, int64_t src_bs, float* dst, int batch, int channels,
+                      int frames, bool reverse, cudaStream_t stream);
+int cond_vectors(const float* w, const float* bias, const float* g, int n_embed, int rows, float* out,
+                 cudaStream_t stream);
+int reflect_row(void* base, int64_t bstride_bytes, int row_bytes, int batch, cudaStream_t stream);
+
+}  // namespace qvc

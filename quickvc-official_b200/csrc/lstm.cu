@@ -1,0 +1,294 @@
+// lstm.cu -- SpeakerEncoder (models.py:507-546) as a persistent-RNN.
+//
+// Per layer: (1) the input projection W_ih x_t + b for every step at once (one exact-fp32 series
+// GEMM), (2) a persistent recurrent kernel: a thread-block cluster of 8 CTAs keeps the layer's
+// 1 MB W_hh resident in shared memory (128 KB slice = 32 hidden units x 4 gates per CTA) for all
+// steps; each step every CTA computes its 32 units for up to 8 sequences, pushes the new h slice
+// into the other CTAs' shared memory (DSMEM) and the cluster barrier closes the step.
+// (3) a small finishing kernel: Linear, ReLU, L2-normalise, mean over the windows.
+// All arithmetic is fp32 FMA: the recurrence amplifies operand rounding, and the whole encoder is
+// 2.4 % of the path's FLOPs.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace qvc {
+
+namespace {
+
+constexpr int HID = 256;
+constexpr int GATES = 4 * HID;
+constexpr int CLUSTER = 8;
+constexpr int UNITS_PER_CTA = HID / CLUSTER;   // 32
+constexpr int MAXSEQ = 8;                      // sequences per cluster
+constexpr int REC_THREADS = 256;
+constexpr size_t REC_SMEM = (size_t)UNITS_PER_CTA * 4 * HID * sizeof(float)      // W_hh slice
+                            + (size_t)2 * MAXSEQ * HID * sizeof(float);          // h double buffer
+
+struct RecParams {
+  const float* w_hh;      // (1024, 256)
+  const float* gx;        // [rows][1024] input projection (bias included)
+  int32_t nseq, steps;
+  int32_t row_stride;     // first gx row of sequence s is s*row_stride ...
+  int32_t last_row;       // ... except, when >= 0, the last sequence starts here
+  float* hseq;            // [nseq][steps][256] or NULL
+  float* hlast;           // [nseq][256] or NULL
+};
+
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(REC_THREADS, 1)
+lstm_recurrent_kernel(const RecParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* Wsm = smem;                                        // [32 units][4 gates][256]
+  float* hbuf = smem + UNITS_PER_CTA * 4 * HID;             // [2][MAXSEQ][256]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int group = blockIdx.x / CLUSTER;                   // which block of <= 8 sequences
+  const int s_base = group * MAXSEQ;
+  const int ns = min(MAXSEQ, p.nseq - s_base);
+  const int tid = threadIdx.x;
+  const int ks = tid & 7;                                   // k-slice / sequence owned in the update
+  const int u = tid >> 3;                                   // local hidden unit
+  const int U = rank * UNITS_PER_CTA + u;                   // global hidden unit
+
+  // resident weights: rows (gate*256 + U) of W_hh
+  for (int i = tid; i < UNITS_PER_CTA * 4 * (HID / 4); i += REC_THREADS) {
+    const int k4 = i % (HID / 4);
+    const int g = (i / (HID / 4)) & 3;
+    const int uu = i / (HID);                               // (HID/4)*4 entries per unit
+    const float4 v = *reinterpret_cast<const float4*>(
+        p.w_hh + ((int64_t)(g * HID + rank * UNITS_PER_CTA + uu)) * HID + 4 * k4);
+    *reinterpret_cast<float4*>(Wsm + ((uu * 4 + g) * HID) + 4 * k4) = v;
+  }
+  for (int i = tid; i < 2 * MAXSEQ * HID; i += REC_THREADS) hbuf[i] = 0.f;
+
+  // sequence owned by this lane in the cell update
+  const int s_own = ks;
+  const bool own = s_own < ns;
+  int64_t gx_row0 = 0;
+  if (own) {
+    const int sg = s_base + s_own;
+    gx_row0 = (p.last_row >= 0 && sg == p.nseq - 1) ? p.last_row : (int64_t)sg * p.row_stride;
+  }
+  float c_state = 0.f;
+  float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (own) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) gxv[g] = __ldg(p.gx + gx_row0 * GATES + g * HID + U);
+  }
+  cluster.sync();
+
+  float* remote[CLUSTER];
+#pragma unroll
+  for (int r = 0; r < CLUSTER; ++r) remote[r] = cluster.map_shared_rank(hbuf, r);
+
+  for (int t = 0; t < p.steps; ++t) {
+    const float* hc = hbuf + (t & 1) * MAXSEQ * HID;
+    float acc[4][MAXSEQ];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int s = 0; s < MAXSEQ; ++s) acc[g][s] = 0.f;
+
+#pragma unroll 2
+    for (int kk = 0; kk < HID / 32; ++kk) {
+      const int k = kk * 32 + ks * 4;
+      float4 wv[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) wv[g] = *reinterpret_cast<const float4*>(Wsm + (u * 4 + g) * HID + k);
+#pragma unroll
+      for (int s = 0; s < MAXSEQ; ++s) {
+        if (s < ns) {
+          const float4 hv = *reinterpret_cast<const float4*>(hc + s * HID + k);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            acc[g][s] = fmaf(wv[g].x, hv.x, acc[g][s]);
+            acc[g][s] = fmaf(wv[g].y, hv.y, acc[g][s]);
+            acc[g][s] = fmaf(wv[g].z, hv.z, acc[g][s]);
+            acc[g][s] = fmaf(wv[g].w, hv.w, acc[g][s]);
+          }
+        }
+      }
+    }
+    // reduce-scatter over the 8 k-slice lanes: lane ks ends with the full sums of sequence ks
+    float gate[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v4[4], v2[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float keep = (ks & 4) ? acc[g][4 + i] : acc[g][i];
+        const float send = (ks & 4) ? acc[g][i] : acc[g][4 + i];
+        v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = (ks & 2) ? v4[2 + i] : v4[i];
+        const float send = (ks & 2) ? v4[i] : v4[2 + i];
+        v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const float keep = (ks & 1) ? v2[1] : v2[0];
+        const float send = (ks & 1) ? v2[0] : v2[1];
+        gate[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+    }
+    float h_new = 0.f;
+    if (own) {
+      const float ig = sigmoid_acc(gate[0] + gxv[0]);
+      const float fg = sigmoid_acc(gate[1] + gxv[1]);
+      const float gg = tanhf(gate[2] + gxv[2]);
+      const float og = sigmoid_acc(gate[3] + gxv[3]);
+      c_state = fg * c_state + ig * gg;
+      h_new = og * tanhf(c_state);
+      const int off = ((t + 1) & 1) * MAXSEQ * HID + s_own * HID + U;
+#pragma unroll
+      for (int r = 0; r < CLUSTER; ++r) remote[r][off] = h_new;
+      if (p.hseq) p.hseq[((int64_t)(s_base + s_own) * p.steps + t) * HID + U] = h_new;
+      if (p.hlast && t == p.steps - 1) p.hlast[(int64_t)(s_base + s_own) * HID + U] = h_new;
+      if (t + 1 < p.steps) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gxv[g] = __ldg(p.gx + (gx_row0 + t + 1) * GATES + g * HID + U);
+      }
+    }
+    cluster.sync();
+  }
+}
+
+// embed[e][n] = mean_w normalise(relu(lin_w h[w] + lin_b))   (models.py:517-518, 540)
+__global__ void __launch_bounds__(HID) spk_finish_kernel(const float* hlast, const float* lin_w,
+                                                         const float* lin_b, int seq_per_embed,
+                                                         float* g_out) {
+  __shared__ float hs[HID];
+  __shared__ float red[HID / 32];
+  const int e = blockIdx.x, n = threadIdx.x;
+  float mean = 0.f;
+  for (int w = 0; w < seq_per_embed; ++w) {
+    __syncthreads();
+    hs[n] = hlast[((int64_t)e * seq_per_embed + w) * HID + n];
+    __syncthreads();
+    float a = lin_b[n];
+    const float4* wr = reinterpret_cast<const float4*>(lin_w + (int64_t)n * HID);
+#pragma unroll 4
+    for (int k4 = 0; k4 < HID / 4; ++k4) {
+      const float4 wv = __ldg(wr + k4);
+      a = fmaf(wv.x, hs[4 * k4], a);
+      a = fmaf(wv.y, hs[4 * k4 + 1], a);
+      a = fmaf(wv.z, hs[4 * k4 + 2], a);
+      a = fmaf(wv.w, hs[4 * k4 + 3], a);
+    }
+    a = fmaxf(a, 0.f);
+    float sq = a * a;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((n & 31) == 0) red[n >> 5] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < HID / 32; ++i) tot += red[i];
+    mean += a / sqrtf(tot);
+  }
+  g_out[(int64_t)e * HID + n] = mean / (float)seq_per_embed;
+}
+
+struct SpkPlan {
+  int nseq, steps, n_embed, seq_per_embed, row_stride, last_row;
+  size_t off_mel, off_gx, off_hseq, off_hlast, total;
+};
+
+SpkPlan make_plan(int bm, int tm) {
+  SpkPlan pl;
+  if (tm > 128) {
+    pl.nseq = (tm - 128 + 63) / 64 + 1;       // len(range(0, tm-128, 64)) + the last window
+    pl.steps = 128;
+    pl.n_embed = 1;
+    pl.seq_per_embed = pl.nseq;
+    pl.row_stride = 64;
+    pl.last_row = tm - 128;
+  } else {
+    pl.nseq = bm;
+    pl.steps = tm;
+    pl.n_embed = bm;
+    pl.seq_per_embed = 1;
+    pl.row_stride = tm;
+    pl.last_row = -1;
+  }
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = 0;
+  pl.off_mel = o;   o += up((size_t)bm * tm * 80 * 4);
+  const size_t gx_rows = (size_t)pl.nseq * pl.steps > (size_t)bm * tm ? (size_t)pl.nseq * pl.steps : (size_t)bm * tm;
+  pl.off_gx = o;    o += up(gx_rows * GATES * 4);
+  pl.off_hseq = o;  o += up((size_t)pl.nseq * pl.steps * HID * 4);
+  pl.off_hlast = o; o += up((size_t)pl.nseq * HID * 4);
+  pl.total = o;
+  return pl;
+}
+
+}  // namespace
+
+}  // namespace qvc
+
+extern "C" size_t qvc_spk_workspace_bytes(int bm, int tm) {
+  if (bm <= 0 || tm <= 0) return 0;
+  return qvc::make_plan(bm, tm).total;
+}
+
+extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm, int tm, float* g_out,
+                             void* workspace, size_t workspace_bytes, qvc_stream_t stream_) {
+  using namespace qvc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QVC_REQUIRE(w && mel && g_out && workspace, "qvc_spk_embed: null pointer");
+  QVC_REQUIRE(bm >= 1 && tm >= 1, "qvc_spk_embed: bad shape (%d, 80, %d)", bm, tm);
+  // the reference stacks (W, Bm, 128, 80).squeeze(1): Bm > 1 is a 4-D LSTM input (models.py:536)
+  QVC_REQUIRE(tm <= 128 || bm == 1, "qvc_spk_embed: mel longer than 128 frames must have batch 1 (got %d)", bm);
+  const SpkPlan pl = make_plan(bm, tm);
+  if (workspace_bytes < pl.total) {
+    set_error("qvc_spk_embed: workspace %zu < %zu", workspace_bytes, pl.total);
+    return QVC_ERR_WORKSPACE;
+  }
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* mel_sm = reinterpret_cast<float*>(ws + pl.off_mel);
+  float* gx = reinterpret_cast<float*>(ws + pl.off_gx);
+  float* hseq = reinterpret_cast<float*>(ws + pl.off_hseq);
+  float* hlast = reinterpret_cast<float*>(ws + pl.off_hlast);
+
+  QVC_PROPAGATE(qvc_to_series_major(mel, mel_sm, bm, 80, tm, QVC_OPF_F32, stream_));
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
+    attr_set = true;
+  }
+
+  for (int layer = 0; layer < 3; ++layer) {
+    // input projection for every step: gx = W_ih x + (b_ih + b_hh)
+    qvc_conv_args a{};
+    const int rows = layer == 0 ? bm * tm : pl.nseq * pl.steps;
+    a.x = qvc_tensor{layer == 0 ? (void*)mel_sm : (void*)hseq, 0, layer == 0 ? 80 : HID, 0};
+    a.batch = 1; a.x_rows = rows; a.out_rows = rows;
+    a.cin = layer == 0 ? 80 : HID;
+    a.w = w->w_ih[layer]; a.bias = w->bias[layer]; a.bias_bstride = 0;
+    a.cout = GATES; a.k = 1; a.dil = 1; a.pad_left = 0;
+    a.epilogue = QVC_EPI_LINEAR; a.nseg = 1;
+    a.seg[0].col0 = 0; a.seg[0].ncols = GATES; a.seg[0].alpha = 1.f; a.seg[0].beta = 1.f; a.seg[0].slope = 1.f;
+    a.seg[0].raw = qvc_tensor{gx, 0, GATES, 0};
+    a.opformat = QVC_OPF_F32; a.backend = QVC_BACKEND_FMA;
+    QVC_PROPAGATE(launch_conv_fma(a, stream));
+
+    RecParams rp;
+    rp.w_hh = w->w_hh[layer];
+    rp.gx = gx;
+    rp.nseq = pl.nseq; rp.steps = pl.steps;
+    rp.row_stride = layer == 0 ? pl.row_stride : pl.steps;
+    rp.last_row = layer == 0 ? pl.last_row : -1;
+    rp.hseq = layer < 2 ? hseq : nullptr;
+    rp.hlast = layer == 2 ? hlast : nullptr;
+    const int groups = (pl.nseq + MAXSEQ - 1) / MAXSEQ;
+    lstm_recurrent_kernel<<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp);
+    QVC_PROPAGATE(post_launch("lstm_recurrent_kernel"));
+  }
+  spk_finish_kernel<<<pl.n_embed, HID, 0, stream>>>(hlast, w->lin_w, w->lin_b, pl.seq_per_embed, g_out);
+  return post_launch("spk_finish_kernel");
+}

@@ -1,0 +1,89 @@
+"""Drop-in boundary: constructor contract, state_dict layout, C-ABI exports (no GPU needed)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from conftest import REFERENCE, ROOT
+from quickvc_official_b200 import SynthesizerTrn, capi
+
+
+def test_state_dict_layout_matches_reference(shapes, model_cfg):
+    net = SynthesizerTrn(641, 32, **model_cfg)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert len(got) == 467
+    assert list(got) == list(shapes)           # same keys in the same order
+    assert got == shapes
+    n_inf = sum(v.numel() for k, v in net.state_dict().items() if not k.startswith("enc_q."))
+    assert sum(p.numel() for p in net.parameters()) == 40032285 - 16 - 64   # buffers are not parameters
+    assert n_inf > 31e6
+
+
+def test_load_state_dict_roundtrip(sd, model_cfg):
+    net = SynthesizerTrn(641, 32, **model_cfg)
+    net.load_state_dict(sd)                    # strict
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_constructor_contract(model_cfg):
+    bad = dict(model_cfg, ms_istft_vits=False)
+    with pytest.raises(RuntimeError):          # models.py:589
+        SynthesizerTrn(641, 32, **bad)
+    with pytest.raises(AssertionError):        # models.py:574-575
+        SynthesizerTrn(641, 32, **model_cfg, resblock="2")
+    SynthesizerTrn(641, 32, **model_cfg, resblock="1", n_heads=2, p_dropout=0.1)   # legacy keys are swallowed
+    with pytest.raises(NotImplementedError):
+        SynthesizerTrn(641, 32, **dict(model_cfg, hidden_channels=128))
+    with pytest.raises(ValueError):
+        SynthesizerTrn(641, 32, **model_cfg, precision="fp8")
+
+
+def test_infer_has_no_cpu_fallback(sd, model_cfg):
+    net = SynthesizerTrn(641, 32, **model_cfg).eval()
+    with pytest.raises(capi.QvcError):
+        net.infer(torch.zeros(1, 256, 8), torch.zeros(1, 80, 130))
+
+
+def test_forward_is_out_of_scope(model_cfg):
+    net = SynthesizerTrn(641, 32, **model_cfg)
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 256, 8), torch.zeros(1, 641, 8), torch.zeros(1, 80, 8))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "qvc_b200.h")).read()
+    declared = set(re.findall(r"\b(qvc_[a-z0-9_]+)\s*\(", header))
+    declared -= {"qvc_layer_index_"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    lib = capi.load()                          # dlopen + bind all; raises on a missing symbol
+    assert lib.qvc_abi_version() == capi.QVC_ABI_VERSION
+    raw = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+
+
+def test_struct_sizes_match_header():
+    # sizes the C compiler produces for the same declarations (LP64)
+    assert ctypes.sizeof(capi.Tensor) == 24
+    assert ctypes.sizeof(capi.EpiSegment) == 24 + 4 * 24
+    assert ctypes.sizeof(capi.Layer) == 40
+    assert ctypes.sizeof(capi.ConvArgs) == 24 + 16 + 24 + 16 + 8 + 2 * 120 + 3 * 24 + 8
+    assert ctypes.sizeof(capi.Model) == 16 + 114 * 40 + 24 + 11 * 8 + 2 * 8
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted")
+def test_seeded_init_equals_reference(model_cfg):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    models = make_golden.load_reference()
+    torch.manual_seed(0)
+    ref = models.SynthesizerTrn(641, 32, **model_cfg).state_dict()
+    torch.manual_seed(0)
+    ours = SynthesizerTrn(641, 32, **model_cfg).state_dict()
+    assert list(ref) == list(ours)
+    for k in ref:
+        assert torch.equal(ref[k], ours[k]), k

@@ -1,0 +1,90 @@
+"""Host-side logic without a GPU: fold.py plus the engine's sequencing (emulated on the CPU by
+tests/emulate.py) against the oracle, per stage, in every operand format."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+from conftest import GOLDEN_CASES, load_golden
+from emulate import Emu
+from oracle import qvc_oracle
+from quickvc_official_b200 import capi, fold
+
+
+def test_round_tf32_matches_definition():
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -1.0 - 2 ** -11, 3.14159265, 1e-20, 0.0])
+    r = fold.round_tf32(x)
+    assert (r.view(torch.int32) & 0x1FFF).abs().sum() == 0          # 13 low mantissa bits cleared
+    assert r[1] == 1.0 + 2 ** -10 and r[3] == -1.0 - 2 ** -10        # ties away from zero
+    assert ((r - x).abs() <= x.abs() * 2 ** -11 + 1e-45).all()
+
+
+def test_polyphase_transpose_filter():
+    torch.manual_seed(0)
+    for stride, k, pad, opad in ((5, 16, 6, 1), (4, 16, 6, 0)):
+        w = torch.randn(8, 6, k, dtype=torch.float64)
+        x = torch.randn(2, 8, 11, dtype=torch.float64)
+        ref = F.conv_transpose1d(x, w, stride=stride, padding=pad, output_padding=opad)
+        f, pad_left = fold.polyphase_transpose_filter(w, stride, pad)
+        taps = f.shape[1]
+        xt = F.pad(x, (pad_left, taps - 1 - pad_left))
+        y = F.conv1d(xt, f.permute(0, 2, 1))                        # (2, stride*6, 11)
+        y = y.reshape(2, stride, 6, 11).permute(0, 2, 3, 1).reshape(2, 6, 11 * stride)
+        assert ref.shape == y.shape
+        assert (ref - y).abs().max() < 1e-12
+
+
+def test_synthesis_polyphase_general_filter():
+    torch.manual_seed(1)
+    updown = torch.randn(4, 4, 4, dtype=torch.float64)               # a general (not identity) buffer
+    w_syn = torch.randn(1, 4, 63, dtype=torch.float64)
+    y = torch.randn(2, 4, 50, dtype=torch.float64)
+    ref = F.conv1d(F.conv_transpose1d(y, updown * 4, stride=4), w_syn, padding=31)
+    E = fold.synthesis_polyphase(updown, w_syn)
+    wt = torch.flip(E.permute(1, 0, 2), [2]).contiguous()
+    o = F.conv1d(F.pad(y, (8, 8)), wt).transpose(1, 2).reshape(2, 1, -1)
+    assert (ref - o).abs().max() < 1e-11
+
+
+def test_layer_table(sd):
+    f = fold.fold_state_dict(sd, capi.OPF_F32)
+    assert len(f.layers) == capi.QVC_NUM_LAYERS
+    names = [L["name"] for L in f.layers]
+    assert names[0] == "enc_p.pre" and names[33] == "enc_p.proj" and names[74] == "dec.conv_pre"
+    assert names[75] == "dec.ups.0" and names[113] == "dec.post" and names[34] == "flow.0.pre"
+    assert (f.layers[75]["k"], f.layers[75]["pad_left"], f.layers[75]["cout"]) == (4, 1, 1280)
+    assert (f.layers[76]["k"], f.layers[76]["pad_left"], f.layers[76]["cout"]) == (5, 2, 512)
+    assert f.layers[113]["cout"] == 80                                # 72 padded to a multiple of 16
+    for L in f.layers:
+        assert L["cin"] % 16 == 0 and L["cout"] % 16 == 0, L["name"]
+    assert f.tensors["cond_w"].shape == (fold.COND_ROWS, 256)
+    assert f.tensors["tail.synth"].shape == (4, 4, 17)
+
+
+@pytest.mark.parametrize("case", ["small", "shortmel"])
+def test_emulated_engine_fp32_matches_oracle_and_golden(case, sd):
+    b, t, bm, tm = GOLDEN_CASES[case]
+    unit, mel, noise = synth.synthetic_inputs(b, t, bm, tm, 0)
+    taps = {}
+    wave = Emu(sd, capi.OPF_F32).infer(unit, mel, noise, taps)
+    gold = load_golden(case)
+    for name, ref in gold.items():
+        assert taps[name].shape == ref.shape, name
+        assert synth.rel_l2(taps[name], ref) < 2e-5, (name, synth.rel_l2(taps[name], ref))
+    assert synth.max_abs(wave, gold["wave"]) < 2e-6
+
+
+# North-star tolerances: fp32 mode (TF32 operands, fp32 accumulate) waveform max-abs 1e-4 and
+# per-stage relative 1e-3; bf16 mode is reported with its own tolerance.
+@pytest.mark.parametrize("opf,wave_tol,stage_tol", [(capi.OPF_TF32, 1e-4, 1e-3), (capi.OPF_BF16, 2e-3, 1.5e-2)])
+def test_emulated_engine_reduced_operands_within_tolerance(opf, wave_tol, stage_tol, sd):
+    b, t, bm, tm = GOLDEN_CASES["small"]
+    unit, mel, noise = synth.synthetic_inputs(b, t, bm, tm, 0)
+    ref = {}
+    qvc_oracle.infer(sd, unit, mel, noise, dtype=torch.float64, taps=ref)
+    taps = {}
+    wave = Emu(sd, opf).infer(unit, mel, noise, taps)
+    worst = max(synth.rel_l2(taps[n], ref[n]) for n in qvc_oracle.TAP_NAMES)
+    err = synth.max_abs(wave, ref["wave"])
+    print(f"opformat {opf}: wave max-abs {err:.3e}, worst stage rel-L2 {worst:.3e}")
+    assert err < wave_tol and worst < stage_tol
