@@ -1,0 +1,210 @@
+"""Kernel-level parity on a B200, through the C ABI: series convolution (both back ends, every
+epilogue and operand format), layout helpers, fused tail, persistent-RNN speaker encoder."""
+import ctypes as C
+
+import pytest
+import torch
+
+import synth
+from gpu_util import conv1d, op_dtype, ref_conv, stream, to_op, tref
+from oracle import qvc_oracle
+from quickvc_official_b200 import capi, fold
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+BACKENDS = [("fma", capi.BACKEND_FMA, capi.OPF_F32), ("fma", capi.BACKEND_FMA, capi.OPF_TF32),
+            ("fma", capi.BACKEND_FMA, capi.OPF_BF16),
+            ("tc", capi.BACKEND_TCGEN05, capi.OPF_TF32), ("tc", capi.BACKEND_TCGEN05, capi.OPF_BF16)]
+IDS = ["fma-f32", "fma-tf32", "fma-bf16", "tc-tf32", "tc-bf16"]
+
+
+def _tol(opf):
+    # accumulation-order noise only: operands are pre-rounded on both sides
+    return 2e-5 if opf != capi.OPF_BF16 else 1e-2
+
+
+# (B, rows, cin, cout, k, dil): shapes of every layer family on the path plus ragged edge cases
+GEOMS = [
+    (2, 24, 256, 192, 1, 1),      # enc_p.pre
+    (2, 37, 192, 192, 1, 1),      # flow pre/post (zero-embedded), ragged rows
+    (1, 200, 192, 512, 7, 1),     # dec.conv_pre
+    (2, 130, 256, 256, 3, 1),     # MRF-1 k3
+    (1, 300, 256, 256, 11, 5),    # MRF-1 k11 dilation 5 (largest halo)
+    (2, 515, 128, 128, 7, 3),     # MRF-2 k7 dilation 3
+    (1, 129, 128, 80, 7, 1),      # conv_post (72 padded to 80)
+    (3, 50, 512, 1280, 4, 1),     # ups.0 polyphase
+    (1, 1, 192, 192, 5, 1),       # a single row
+    (2, 5, 128, 128, 11, 5),      # series shorter than the filter span
+]
+
+
+@pytest.mark.parametrize("geom", GEOMS, ids=[f"B{g[0]}_R{g[1]}_{g[2]}to{g[3]}_k{g[4]}d{g[5]}" for g in GEOMS])
+@pytest.mark.parametrize("be", BACKENDS, ids=IDS)
+def test_conv_linear(geom, be):
+    _, backend, opf = be
+    B, rows, cin, cout, k, dil = geom
+    g = torch.Generator(device="cpu").manual_seed(hash(geom) & 0xffff)
+    x = to_op(torch.randn(B, rows, cin, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(cout, k, cin, generator=g) / (cin * k) ** 0.5, opf).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    res = torch.randn(B, rows, cout, generator=g).to(DEV)
+    accin = torch.randn(B, rows, cout, generator=g).to(DEV)
+    raw = torch.full((B, rows, cout), float("nan"), device=DEV)
+    op = torch.zeros(B, rows, cout, device=DEV, dtype=op_dtype(opf))
+    pad_left = (k - 1) * dil // 2
+    conv1d(x, w, bias, k=k, dil=dil, pad_left=pad_left, out_rows=rows, opf=opf, backend=backend,
+           segs=[dict(col0=0, ncols=cout, alpha=-1.0, beta=1.0 / 3, slope=0.1, res=res, accin=accin, raw=raw, op=op)])
+    torch.cuda.synchronize()
+    acc = ref_conv(x.cpu().float(), w.cpu().float(), k, dil, pad_left, rows)
+    want = accin.cpu().double() + (1.0 / 3) * (-(acc + bias.cpu().double()) + res.cpu().double())
+    scale = float(want.abs().max())
+    assert float((raw.cpu().double() - want).abs().max()) < _tol(opf) * scale
+    want_op = torch.where(want > 0, want, want * 0.1)
+    err_op = float((op.cpu().double() - want_op).abs().max())
+    assert err_op < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11 if opf == capi.OPF_TF32 else 0)) * scale
+    if opf == capi.OPF_TF32:        # the operand copy must sit on the TF32 grid
+        assert int((op.view(torch.int32) & 0x1FFF).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("be", BACKENDS, ids=IDS)
+def test_conv_two_segments_wn_res_skip(be):
+    _, backend, opf = be
+    B, rows, H = 2, 70, 192
+    g = torch.Generator(device="cpu").manual_seed(5)
+    acts = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(2 * H, 1, H, generator=g) / H ** 0.5, opf).to(DEV)
+    bias = torch.randn(2 * H, generator=g).to(DEV)
+    x = torch.randn(B, rows, H, generator=g).to(DEV)
+    skip = torch.randn(B, rows, H, generator=g).to(DEV)
+    x0, skip0 = x.clone(), skip.clone()
+    xo = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+    conv1d(acts, w, bias, k=1, dil=1, pad_left=0, out_rows=rows, opf=opf, backend=backend,
+           segs=[dict(col0=0, ncols=H, res=x, raw=x, op=xo), dict(col0=H, ncols=H, accin=skip, raw=skip)])
+    torch.cuda.synchronize()
+    acc = ref_conv(acts.cpu().float(), w.cpu().float(), 1, 1, 0, rows) + bias.cpu().double()
+    assert float((x.cpu().double() - (x0.cpu().double() + acc[..., :H])).abs().max()) < _tol(opf) * 4
+    assert float((skip.cpu().double() - (skip0.cpu().double() + acc[..., H:])).abs().max()) < _tol(opf) * 4
+
+
+@pytest.mark.parametrize("be", BACKENDS, ids=IDS)
+@pytest.mark.parametrize("per_utt_bias", [False, True])
+def test_conv_gate(be, per_utt_bias):
+    _, backend, opf = be
+    B, rows, H, k = 3, 45, 192, 5
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(2 * H, k, H, generator=g) / (H * k) ** 0.5, opf).to(DEV)
+    bias = torch.randn(B if per_utt_bias else 1, 2 * H, generator=g).to(DEV)
+    op = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+    raw = torch.zeros(B, rows, H, device=DEV)
+    conv1d(x, w, bias, k=k, dil=1, pad_left=2, out_rows=rows, opf=opf, backend=backend, epilogue=capi.EPI_GATE,
+           segs=[dict(col0=0, ncols=H, op=op, raw=raw)], bias_bstride=2 * H if per_utt_bias else 0)
+    torch.cuda.synchronize()
+    a = ref_conv(x.cpu().float(), w.cpu().float(), k, 1, 2, rows) + bias.cpu().double().reshape(-1, 1, 2 * H)
+    want = torch.tanh(a[..., :H]) * torch.sigmoid(a[..., H:])
+    assert float((raw.cpu().double() - want).abs().max()) < max(_tol(opf), 1e-5)
+    assert float((op.cpu().double() - want).abs().max()) < max(_tol(opf), 1e-5) + 2 ** -8
+
+
+@pytest.mark.parametrize("be", BACKENDS, ids=IDS)
+def test_conv_sample(be):
+    _, backend, opf = be
+    B, rows, H = 2, 33, 192
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(2 * H, 1, H, generator=g) / H ** 0.5, opf).to(DEV)
+    bias = (0.1 * torch.randn(2 * H, generator=g)).to(DEV)
+    noise = torch.randn(B, rows, H, generator=g).to(DEV)
+    z = torch.zeros(B, rows, H, device=DEV)
+    m = torch.zeros(B, rows, H, device=DEV)
+    lg = torch.zeros(B, rows, H, device=DEV)
+    zo = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+    conv1d(x, w, bias, k=1, dil=1, pad_left=0, out_rows=rows, opf=opf, backend=backend, epilogue=capi.EPI_SAMPLE,
+           segs=[dict(col0=0, ncols=H, raw=z, op=zo)], noise=noise, aux0=m, aux1=lg)
+    torch.cuda.synchronize()
+    a = ref_conv(x.cpu().float(), w.cpu().float(), 1, 1, 0, rows) + bias.cpu().double()
+    want = a[..., :H] + noise.cpu().double() * torch.exp(a[..., H:])
+    tol = max(_tol(opf), 1e-5) * float(want.abs().max())
+    assert float((z.cpu().double() - want).abs().max()) < tol
+    assert float((m.cpu().double() - a[..., :H]).abs().max()) < tol
+    assert float((lg.cpu().double() - a[..., H:]).abs().max()) < tol
+
+
+def test_layout_roundtrip():
+    lib = capi.load()
+    x = torch.randn(3, 80, 77, device=DEV)
+    sm = torch.empty(3, 77, 80, device=DEV)
+    capi.check(lib.qvc_to_series_major(x.data_ptr(), sm.data_ptr(), 3, 80, 77, capi.OPF_F32, stream()), "to")
+    assert torch.equal(sm, x.transpose(1, 2).contiguous())
+    back = torch.empty_like(x)
+    capi.check(lib.qvc_from_series_major(sm.data_ptr(), 80, back.data_ptr(), 3, 80, 77, stream()), "from")
+    assert torch.equal(back, x)
+    t32 = torch.empty(3, 77, 80, device=DEV)
+    capi.check(lib.qvc_to_series_major(x.data_ptr(), t32.data_ptr(), 3, 80, 77, capi.OPF_TF32, stream()), "to")
+    assert torch.equal(t32.cpu(), fold.round_tf32(x.transpose(1, 2).contiguous().cpu()))
+    b16 = torch.empty(3, 77, 80, device=DEV, dtype=torch.bfloat16)
+    capi.check(lib.qvc_to_series_major(x.data_ptr(), b16.data_ptr(), 3, 80, 77, capi.OPF_BF16, stream()), "to")
+    assert torch.equal(b16, x.transpose(1, 2).contiguous().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("frames,batch", [(2, 1), (17, 3), (481, 2), (1001, 1)])
+def test_tail_matches_oracle(frames, batch, sd):
+    lib = capi.load()
+    g = torch.Generator(device="cpu").manual_seed(frames)
+    post = 0.5 * torch.randn(batch, 72, frames, generator=g)
+    f = fold.fold_state_dict({k: v for k, v in sd.items() if not k.startswith("enc_q.")}, capi.OPF_F32)
+    tw = capi.TailWeights(f.tensors["tail.window"].to(DEV).data_ptr(), 0)
+    win, syn = f.tensors["tail.window"].to(DEV), f.tensors["tail.synth"].to(DEV)
+    tw = capi.TailWeights(win.data_ptr(), syn.data_ptr())
+    post_sm = post.transpose(1, 2).contiguous().to(DEV)
+    wave = torch.full((batch, 1, 16 * (frames - 1)), float("nan"), device=DEV)
+    ymb = torch.full((batch, 4, 4 * (frames - 1)), float("nan"), device=DEV)
+    capi.check(lib.qvc_tail(C.byref(tw), post_sm.data_ptr(), 72, batch, frames, wave.data_ptr(), ymb.data_ptr(),
+                            stream()), "qvc_tail")
+    torch.cuda.synchronize()
+    # oracle: the decoder code after subband_conv_post (models.py:390-406)
+    p = qvc_oracle._P(sd, torch.float64)
+    x = post.double().reshape(batch, 4, 18, frames)
+    y = qvc_oracle.istft_closed_form(x[:, :, :9].reshape(batch * 4, 9, frames), x[:, :, 9:].reshape(batch * 4, 9, frames),
+                                     p.raw("dec.stft.window")).reshape(batch, 4, -1)
+    import torch.nn.functional as F
+    up = F.conv_transpose1d(y, p.raw("dec.updown_filter") * 4, stride=4)
+    want = F.conv1d(up, p.weight("dec.multistream_conv_post"), padding=31)
+    assert synth.max_abs(ymb, y) < 2e-5 * float(y.abs().max())
+    assert synth.max_abs(wave, want) < 2e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("bm,tm", [(1, 129), (1, 250), (1, 500), (1, 1500), (3, 100), (1, 128), (9, 7)])
+def test_speaker_encoder_matches_oracle(bm, tm, sd):
+    lib = capi.load()
+    f = fold.fold_state_dict({k: v for k, v in sd.items() if not k.startswith("enc_q.")}, capi.OPF_F32)
+    t = {k: v.to(DEV) for k, v in f.tensors.items() if k.startswith("spk.")}
+    sw = capi.SpkWeights()
+    for l in range(3):
+        sw.w_ih[l], sw.w_hh[l], sw.bias[l] = t[f"spk.w_ih.{l}"].data_ptr(), t[f"spk.w_hh.{l}"].data_ptr(), t[f"spk.bias.{l}"].data_ptr()
+    sw.lin_w, sw.lin_b = t["spk.lin_w"].data_ptr(), t["spk.lin_b"].data_ptr()
+    _, mel, _ = synth.synthetic_inputs(1, 1, bm, tm, 11)
+    want = qvc_oracle.embed_utterance(qvc_oracle._P(sd, torch.float64), mel.double())
+    n_embed = want.shape[0]
+    g = torch.full((n_embed, 256), float("nan"), device=DEV)
+    nbytes = int(lib.qvc_spk_workspace_bytes(bm, tm))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=DEV)
+    base = (ws.data_ptr() + 255) & ~255
+    mel_d = mel.to(DEV)
+    capi.check(lib.qvc_spk_embed(C.byref(sw), mel_d.data_ptr(), bm, tm, g.data_ptr(), base, nbytes, stream()), "spk")
+    torch.cuda.synchronize()
+    assert synth.rel_l2(g, want) < 1e-4, synth.rel_l2(g, want)
+
+
+def test_error_reporting():
+    lib = capi.load()
+    a = capi.ConvArgs()
+    assert lib.qvc_conv1d(C.byref(a), stream()) == -1
+    assert b"null" in lib.qvc_last_error()
+    sw = capi.SpkWeights()
+    mel = torch.zeros(2, 80, 200, device=DEV)
+    g = torch.zeros(1, 256, device=DEV)
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
+    assert lib.qvc_spk_embed(C.byref(sw), mel.data_ptr(), 2, 200, g.data_ptr(), ws.data_ptr(), ws.numel(), stream()) == -1
+    assert b"batch 1" in lib.qvc_last_error()
