@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the QuickVC conversion hot path (SynthesizerTrn.infer) on B200.
+
+    python bench.py --gpus N --steps K --warmup W                (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port of the
+                                                                  reference's PyTorch infer, all host threads)
+
+One "step" = one `infer` over one batch of synthetic inputs.  Workload at every N: BASELINE.json
+configs[1], batch 64 x 10 s utterances (T = 500 unit frames, one 10 s target mel), fp32 mode
+(fp32 storage + accumulation, TF32 tensor-core operands), per GPU -- weak scaling, utterances are
+independent so ranks share nothing.  `value` = audio-seconds converted per second by the whole job
+with inputs resident in HBM; `e2e` = the same through the public Python API with pinned host buffers
+(H2D of unit+mel and D2H of the waveform inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FLOP_PER_FRAME = 207.2e6          # conv/linear FLOPs per unit frame per utterance
+FLOP_PER_WINDOW = 356.5e6         # speaker-encoder LSTM FLOPs per 128-frame mel window
+TAIL_BYTES_PER_POST_FRAME = 72 * 4 + 16 * 4   # read 72 fp32 channels, write 16 fp32 samples
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--mel-frames", type=int, default=500)
+    ap.add_argument("--chunk-utts", type=int, default=0)
+    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / latency / tail side measurements")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def model_cfg():
+    with open(os.path.join(ROOT, "tests", "golden", "quickvc_model_config.json")) as f:
+        return json.load(f)
+
+
+def n_windows(tm: int) -> int:
+    return (tm - 128 + 63) // 64 + 1 if tm > 128 else 1
+
+
+def random_init_state_dict(cfg):
+    """Random-init weights of the reference architecture: the drop-in module's seeded constructor (equal to
+    the reference's own under the same seed, tests/test_boundary.py) with the zero-initialised flow `post`
+    layers (modules.py:196-197) re-drawn so the flow is not an identity."""
+    import torch
+    from quickvc_official_b200 import SynthesizerTrn
+    torch.manual_seed(0)
+    net = SynthesizerTrn(641, 32, **cfg)
+    sd = net.state_dict()
+    g = torch.Generator().manual_seed(7)
+    for k in sd:
+        if ".post." in k and k.startswith("flow."):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.05
+    return sd
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm / baseline: the oracle port of the reference's infer, PyTorch fp32 on all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_infer_rate(sd, batch, frames, mel_frames, warmup, steps):
+    import torch
+    import synth
+    from oracle import qvc_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    unit, mel, noise = synth.synthetic_inputs(batch, frames, 1, mel_frames, 3)
+    for _ in range(warmup):
+        qvc_oracle.infer(sd, unit, mel, noise)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        qvc_oracle.infer(sd, unit, mel, noise)
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch * frames / 50.0 / sec, sec
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cfg = model_cfg()
+    sd = random_init_state_dict(cfg)
+    budget = max(1, args.steps + args.warmup)
+    sample = max(1, min(args.cpu_sample_batch, 60 // budget))       # keep the whole run within minutes
+    rate, sec = cpu_infer_rate(sd, sample, args.frames, args.mel_frames, args.warmup, args.steps)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "audio-sec/sec", "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json configs[1]: batch 64 x 10 s utterances, fp32; each CPU step is a bounded "
+                               f"sample of it: {sample} x {args.frames / 50:.0f} s utterances",
+                   "batch": sample, "frames": args.frames, "mel_frames": args.mel_frames},
+        "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} x {args.frames / 50:.0f} s utterances per step, oracle port of the reference's "
+                                   f"PyTorch infer, torch.set_num_threads({cores}), CPU {cpu_model_name()}"},
+        "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import synth  # noqa: F401
+    from quickvc_official_b200 import SynthesizerTrn, capi
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    cfg = model_cfg()
+    sd = random_init_state_dict(cfg)
+
+    def make_net(precision):
+        net = SynthesizerTrn(641, 32, **cfg, precision=precision, chunk_utts=args.chunk_utts).eval()
+        net.load_state_dict(sd)
+        return net.to(dev)
+
+    net = make_net(args.precision)
+    B, T, TM = args.batch, args.frames, args.mel_frames
+    g = torch.Generator().manual_seed(100 + rank)
+    unit_h = torch.randn(B, 256, T, generator=g).pin_memory()
+    mel_h = (torch.randn(1, 80, TM, generator=g) * 2 - 5).pin_memory()
+    noise = torch.randn(B, 192, T, generator=g).to(dev)
+    unit, mel = unit_h.to(dev), mel_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()                       # L2 flush between timed iterations, outside the events
+            starts[i].record()
+            fn()
+            ends[i].record()
+        barrier()
+        per = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        tot = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()) / steps, per
+
+    audio_s = B * T / 50.0
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---- device-resident throughput ----
+    l0 = capi.launch_count()
+    ms, per = timed(lambda: net.infer(unit, mel, noise=noise), args.steps, args.warmup)
+    launches = (capi.launch_count() - l0) // (args.steps + args.warmup)
+    value = world * audio_s / (ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host in, pinned host out ----
+    wave_h = torch.empty(B, 1, 320 * T).pin_memory()
+    unit_d, mel_d = torch.empty_like(unit), torch.empty_like(mel)
+
+    def e2e_step():
+        unit_d.copy_(unit_h, non_blocking=True)
+        mel_d.copy_(mel_h, non_blocking=True)
+        wave_h.copy_(net.infer(unit_d, mel_d), non_blocking=True)      # the user's call: infer(unit, mel)
+
+    ms_e2e, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e_value = world * audio_s / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class (tcgen05 series convolutions: 99.9 % of the FLOPs) ----
+    flops = B * T * FLOP_PER_FRAME + n_windows(TM) * FLOP_PER_WINDOW
+    achieved = flops / (ms * 1e-3) / 1e12
+    tf32 = args.precision != "bf16"
+    peak = pk["bf16_sustained"] * (0.5 if tf32 else 1.0)
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": pk["source"] + ": bf16_tflops_sustained (kernels timed inside a long step)"
+                       + (" x 0.5 -- TF32 operands run at half the bf16 tensor rate and no TF32 figure is measured" if tf32 else ""),
+        "frac_of_bf16_sustained": achieved / pk["bf16_sustained"],
+        "flops_per_step": flops,
+        "note": "whole-step algorithmic FLOPs (207.2 MFLOP per unit frame per utterance + LSTM) over the CUDA-event step time",
+    }
+
+    line = {
+        "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"tf32": "tf32 operands, f32 accumulate/storage", "bf16": "bf16 operands, f32 accumulate",
+                  "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: QuickVC SynthesizerTrn.infer, batch 64 x 10 s utterances, fp32 mode, "
+                               "random-init weights, one 10 s target mel", "batch_per_gpu": B, "frames": T, "mel_frames": TM,
+                   "precision": args.precision, "l2": "flushed (256 MB memset) between timed steps",
+                   "audio_seconds_per_step_per_gpu": audio_s},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": unit_h.numel() * 4 + mel_h.numel() * 4, "d2h_bytes_per_step": wave_h.numel() * 4},
+        "gpu_launches": int(launches) * args.steps,
+        "gpu_launches_per_step": int(launches),
+        "roofline": roofline,
+        "x_realtime_per_gpu": value / world,
+        "step_ms_min_max": [min(per), max(per)],
+    }
+
+    if not args.no_extras and world == 1:
+        import ctypes as C
+        # tail kernel alone: HBM roofline of the fused iSTFT / OLA / synthesis kernel
+        frames_post = 20 * T + 1
+        post = torch.randn(B, frames_post, 72, device=dev) * 0.3
+        wave = torch.empty(B, 1, 320 * T, device=dev)
+        lib = capi.load()
+        model = net._engine._ensure_model(dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        ms_tail, _ = timed(lambda: capi.check(lib.qvc_tail(C.byref(model.tail), post.data_ptr(), 72, B, frames_post,
+                                                           wave.data_ptr(), None, stream), "qvc_tail"), 20, 3)
+        tail_bytes = B * frames_post * TAIL_BYTES_PER_POST_FRAME
+        line["tail_roofline"] = {"bound": "hbm", "achieved": tail_bytes / (ms_tail * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                 "frac": tail_bytes / (ms_tail * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "ms": ms_tail,
+                                 "peak_source": pk["source"]}
+        # the separately reported bf16 mode, and the p50 latency of one 5 s clip
+        if args.precision == "tf32":
+            nb = make_net("bf16")
+            ms_b, _ = timed(lambda: nb.infer(unit, mel, noise=noise), max(3, args.steps // 2), 2)
+            line["bf16_mode"] = {"value": audio_s / (ms_b * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_b,
+                                 "roofline_frac_of_bf16_sustained": flops / (ms_b * 1e-3) / 1e12 / pk["bf16_sustained"],
+                                 "tolerance": "waveform max-abs 2e-3, per-stage rel-L2 1.5e-2 (tests/test_gpu_infer.py)"}
+            del nb
+        u5, m5, n5 = unit[:1, :, :250].contiguous(), mel[:, :, :250].contiguous(), noise[:1, :, :250].contiguous()
+        lat = []
+        for i in range(60):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            net.infer(u5, m5, noise=n5)
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 10:
+                lat.append(s.elapsed_time(e))
+        lat.sort()
+        line["latency_5s_clip_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))]}
+
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        sample = max(1, args.cpu_sample_batch)
+        rate, sec = cpu_infer_rate(sd, sample, T, TM, 1, 2)
+        line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} x {T / 50:.0f} s utterances, oracle port of the reference's PyTorch infer "
+                                          f"(fp32, torch.set_num_threads({cores})), 1 warm-up + 2 timed calls of {sec:.2f} s, "
+                                          f"CPU {cpu_model_name()}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
