@@ -6,8 +6,8 @@
 //   *O buffers: GEMM operands in the model's operand format (TF32-rounded fp32, or bf16), with the
 //               next layer's leaky-relu already applied by the producing epilogue
 // Whole-batch buffers serve the prior encoder and the flow (192 channels at the unit frame rate);
-// the decoder runs per sub-batch of `chunk_utts` utterances so that its working set (the 256- and
-// 128-channel series at 5x / 20x the frame rate) stays resident in the 126 MB L2.
+// the decoder runs per sub-batch of `chunk_utts` utterances (default: the whole batch, bounded only by
+// the workspace size).
 #include "common.cuh"
 #include "engine.h"
 
@@ -50,9 +50,11 @@ struct Buffers {
 int pick_chunk(const qvc_model* m, int B, int T) {
   int cb = m->chunk_utts;
   if (cb <= 0) {
-    // five live 128-channel fp32 series at 20x the frame rate per utterance; aim for ~64 MB
-    const double per_utt = 5.0 * 20.0 * T * C_UP1 * 4.0;
-    cb = (int)(64.0 * 1024 * 1024 / (per_utt > 1 ? per_utt : 1));
+    // Whole batch per launch unless the decoder working set would pass ~24 GB (measured on B200,
+    // profiles/r01_v1_summary.md: sub-batching for L2 residency starves the grid and is 2.2x slower).
+    // Per utterance: ~14 live series of 20 T rows x 128 channels (or 5 T x 256), 4 bytes each.
+    const double per_utt = 14.0 * 20.0 * T * C_UP1 * 4.0;
+    cb = (int)(24.0 * 1024 * 1024 * 1024 / (per_utt > 1 ? per_utt : 1));
     if (cb < 1) cb = 1;
   }
   return cb > B ? B : cb;
