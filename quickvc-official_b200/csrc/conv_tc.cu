@@ -1,19 +1,27 @@
 // conv_tc.cu -- series convolution as an implicit GEMM on the 5th-generation tensor cores
 // (QVC_BACKEND_TCGEN05): TMA -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue.
 //
-//   D[t][n] = sum_{j<k} sum_{c<cin}  X[t + j*dil - pad][c] * W[n][j][c]
-//   A (M = 128 frames per MMA)  = activation rows, K-major (channels contiguous), 128-byte rows
-//   B (N = up to 256 columns)   = folded filter rows [n][j][c], K-major
+//   D[n][t] = sum_{j<k} sum_{c<cin}  W[n][j][c] * X[t + j*dil - pad][c]
+//   A (M = 128 output channels per MMA) = folded filter rows [n][j][c], K-major, 128-byte rows
+//   B (N = up to 256 frames)            = activation rows, K-major (channels contiguous)
 //   one K block = one filter tap j x one 128-byte channel chunk (32 TF32 / 64 bf16 channels)
 //
+// Output channels sit on the TMEM lanes and frames on the TMEM columns.  An epilogue thread therefore
+// owns one output channel and walks over frames, so that a warp touches 32 consecutive channels of
+// one frame per instruction: every residual / skip / noise load and every raw / operand store of the
+// series-major [utterance][frame][channel] tensors is a fully used 128-byte line.  (The v1 kernel had
+// frames on the lanes; its epilogue touched 32 different lines per instruction and ran at 10-20 % of
+// the tensor pipe, profiles/r01_v1_summary.md.)
+//
 // What makes it a convolution rather than im2col + GEMM: the activation chunk is brought in ONCE per
-// channel chunk as a "slab" of (MT*128 + (k-1)*dil) consecutive frames (TMA, 128B swizzle, rows outside
+// channel chunk as a "slab" of (N + (k-1)*dil) consecutive frames (TMA, 128B swizzle, rows outside
 // the utterance zero-filled by the tensor map => the reference's zero padding, no cross-utterance
 // leakage); the k taps are k shared-memory descriptors into the same slab, each shifted by j*dil rows.
-// Only the filter streams from L2, and one filter stage feeds MT accumulator tiles.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
-// epilogue (TMEM -> registers -> fused epilogue of common.cuh -> global).
+// Persistent CTAs (one per SM) walk over tiles (utterance, frame block, output-channel group); TMEM
+// holds two accumulator sets of 256 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
+// epilogue (two warps per TMEM lane quarter, each taking half of the tile's frames).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -25,27 +33,29 @@ namespace qvc {
 
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int ROW_BYTES = 128;            // one swizzle-128B row = one K block of one frame
+constexpr int CHUNK_M = 128;              // output channels per MMA (TMEM lanes)
+constexpr int ROW_BYTES = 128;            // one swizzle-128B row = one K block of one frame / filter row
+constexpr int CHUNK_BYTES = CHUNK_M * ROW_BYTES;
 constexpr int MAX_SMEM = 232448;          // 227 KB
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;
+constexpr int N_EPI_WARPS = 8;
+constexpr int MAXG = 4;                   // output-channel chunks per tile
+constexpr int MAXGROUPS = 8;              // output-channel groups per layer
+constexpr int ACC_COLS = 256;             // TMEM columns per accumulator set
 
 struct alignas(64) TcParams {
   CUtensorMap mx;                          // x as (channel, frame, utterance)
-  CUtensorMap mw;                          // w as (tap*cin + channel, column)
+  CUtensorMap mw;                          // w as (tap*cin + channel, output channel)
   int32_t cin, k, dil, pad_left;
-  int32_t nc;                              // GEMM columns owned by one CTA
-  int32_t nsplit, nchunk;                  // nc = nsplit * nchunk, nchunk = N of one MMA
-  int32_t mt;                              // 128-frame accumulator tiles per CTA
+  int32_t ntime;                           // N: frames per tile (multiple of 32, <= 256)
+  int32_t ntb;                             // frame blocks per utterance
+  int32_t ngroups, ntiles;
+  int32_t gsize[MAXGROUPS];                // chunks of each group
+  int32_t row0[MAXGROUPS][MAXG];           // filter row (GEMM column n) on lane 0 of each chunk
+  int32_t valid[MAXGROUPS][MAXG];          // live lanes of each chunk
   int32_t slab_boxes, slab_box_rows;       // slab = slab_boxes TMA boxes of slab_box_rows frames
-  int32_t w_boxes, w_box_rows;
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes, w_stage_bytes;
-  uint32_t tmem_cols;
-  int32_t desc_mode;                       // 0 (default): base_offset 0 -- measured on B200: the 128B swizzle is a
-                                           // function of the absolute shared-memory address, so a descriptor may start
-                                           // on any 128-byte row of a TMA-written slab; 1 = (addr >> 7) & 7 (wrong, kept
-                                           // only for the experiment recorded in profiles/r01_tc_desc_mode.log)
   EpiParams ep;
 };
 
@@ -60,6 +70,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   // bounded spin: a protocol bug must trap, not hang the GPU
@@ -71,7 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (spins > (1u << 24)) __trap();
+    if (spins > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -110,35 +123,172 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 }
 
 // K-major, 128-byte-swizzled operand: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, int mode) {
+// Measured on B200 (profiles/r01_tc_desc_mode.log): the 128B swizzle is a function of the absolute
+// shared-memory address, so a descriptor may start on any 128-byte row of a TMA-written slab with
+// base_offset 0 -- which is what lets one slab serve all k taps.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
   d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-  if (mode == 1) d |= (uint64_t)((addr >> 7) & 7u) << 49;   // base offset: phase of the start row in the swizzle pattern
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// 32 consecutive TMEM columns of this thread's lane; completion via tmem_wait().
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// exp / sigmoid / tanh on the SFU (ex2.approx, rcp.approx): absolute error of a few 1e-7 on the gate
+// output, two orders below the TF32 rounding of the operand it becomes.  The exact-fp32 FMA back end
+// keeps expf / tanhf.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.f + fast_exp(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * fast_rcp(1.f + fast_exp(2.f * x)); }
+
+// ----------------------------------------------------------------------------------------------
+// epilogues: one thread = one output channel, 32 consecutive frames t .. t+31 (nv of them live)
+// ----------------------------------------------------------------------------------------------
+template <int OPF>
+__device__ __forceinline__ void epi_linear_cols(const EpiSeg& sg, int b, int t, int nv, int c, bool ok,
+                                                float bias_v, uint32_t taddr) {
+  using OT = typename OpType<OPF>::type;
+  float v[32], r[32], a[32];
+  const bool has_res = sg.res.present(), has_acc = sg.accin.present();
+  if (has_res) {
+    const float* rp = sg.res.at<float>(b, t, c);
+    const int64_t ld = sg.res.ld;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) r[i] = (ok && i < nv) ? rp[i * ld] : 0.f;
+  }
+  if (has_acc) {
+    const float* ap = sg.accin.at<float>(b, t, c);
+    const int64_t ld = sg.accin.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = (ok && i < nv) ? ap[i * ld] : 0.f;
+  }
+  tmem_ld32(taddr, v);
+  tmem_wait();
+  const float alpha = sg.alpha, beta = sg.beta;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = alpha * (v[i] + bias_v);
+    if (has_res) x += r[i];
+    v[i] = has_acc ? fmaf(beta, x, a[i]) : beta * x;
+  }
+  if (sg.raw.present()) {
+    float* wp = sg.raw.at<float>(b, t, c);
+    const int64_t ld = sg.raw.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) wp[i * ld] = v[i];
+  }
+  if (sg.op.present()) {
+    OT* op = sg.op.at<OT>(b, t, c);
+    const int64_t ld = sg.op.ld;
+    const float slope = sg.slope;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) op[i * ld] = to_operand<OPF>(leaky(v[i], slope));
+  }
+}
+
+template <int OPF>
+__device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t, int nv, int n, bool ok,
+                                              float bias_lo, float bias_hi, uint32_t taddr_lo, uint32_t taddr_hi) {
+  using OT = typename OpType<OPF>::type;
+  float lo[32], hi[32];
+  tmem_ld32(taddr_lo, lo);
+  tmem_ld32(taddr_hi, hi);
+  tmem_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) lo[i] = fast_tanh(lo[i] + bias_lo) * fast_sigmoid(hi[i] + bias_hi);
+  const EpiSeg& sg = ep.seg[0];
+  if (sg.raw.present()) {
+    float* wp = sg.raw.at<float>(b, t, n);
+    const int64_t ld = sg.raw.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) wp[i * ld] = lo[i];
+  }
+  if (sg.op.present()) {
+    OT* op = sg.op.at<OT>(b, t, n);
+    const int64_t ld = sg.op.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) op[i * ld] = to_operand<OPF>(lo[i]);
+  }
+}
+
+template <int OPF>
+__device__ __forceinline__ void epi_sample_cols(const EpiParams& ep, int b, int t, int nv, int n, bool ok,
+                                                float bias_lo, float bias_hi, uint32_t taddr_lo, uint32_t taddr_hi) {
+  using OT = typename OpType<OPF>::type;
+  float m[32], lg[32], nz[32];
+  {
+    const float* np = ep.noise.at<float>(b, t, n);
+    const int64_t ld = ep.noise.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) nz[i] = (ok && i < nv) ? np[i * ld] : 0.f;
+  }
+  tmem_ld32(taddr_lo, m);
+  tmem_ld32(taddr_hi, lg);
+  tmem_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    m[i] += bias_lo;
+    lg[i] += bias_hi;
+    nz[i] = fmaf(nz[i], fast_exp(lg[i]), m[i]);        // z = m + noise * exp(logs)   (models.py:94)
+  }
+  if (ep.aux0.present()) {
+    float* wp = ep.aux0.at<float>(b, t, n);
+    const int64_t ld = ep.aux0.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) wp[i * ld] = m[i];
+  }
+  if (ep.aux1.present()) {
+    float* wp = ep.aux1.at<float>(b, t, n);
+    const int64_t ld = ep.aux1.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) wp[i * ld] = lg[i];
+  }
+  const EpiSeg& sg = ep.seg[0];
+  if (sg.raw.present()) {
+    float* wp = sg.raw.at<float>(b, t, n);
+    const int64_t ld = sg.raw.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) wp[i * ld] = nz[i];
+  }
+  if (sg.op.present()) {
+    OT* op = sg.op.at<OT>(b, t, n);
+    const int64_t ld = sg.op.ld;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (ok && i < nv) op[i * ld] = to_operand<OPF>(nz[i]);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -155,25 +305,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   const uint32_t slab0 = smem_base;
   const uint32_t w0 = slab0 + p.slab_stages * p.slab_stage_bytes;
   const uint32_t bar0 = w0 + p.w_stages * p.w_stage_bytes;
-  // barrier layout: full_slab[SS] empty_slab[SS] full_w[WS] empty_w[WS] tmem_full, then the TMEM base word
+  // barrier layout: full_slab[SS] empty_slab[SS] full_w[WS] empty_w[WS] tmem_full[2] tmem_empty[2], TMEM base word
   const uint32_t full_slab = bar0, empty_slab = full_slab + 8 * p.slab_stages;
   const uint32_t full_w = empty_slab + 8 * p.slab_stages, empty_w = full_w + 8 * p.w_stages;
-  const uint32_t tmem_full = empty_w + 8 * p.w_stages;
-  const uint32_t tmem_slot = tmem_full + 8;
+  const uint32_t tmem_full = empty_w + 8 * p.w_stages, tmem_empty = tmem_full + 16;
+  const uint32_t tmem_slot = tmem_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.x * p.mt * TILE_M;
-  const int n0 = blockIdx.y * p.nc;
   const int n_cchunks = p.cin / KC;
+  const int N = p.ntime;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * p.slab_stages + 2 * p.w_stages + 1; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 2 * p.slab_stages + 2 * p.w_stages + 2; ++i) mbar_init(bar0 + 8 * i, 1);
+    mbar_init(tmem_empty, N_EPI_WARPS);
+    mbar_init(tmem_empty + 8, N_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * ACC_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -187,93 +337,133 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mx) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
       const uint32_t slab_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
-      const uint32_t w_bytes = (uint32_t)p.nc * ROW_BYTES;
-      int wit = 0;
-      for (int cc = 0; cc < n_cchunks; ++cc) {
-        const int s = cc % p.slab_stages;
-        const uint32_t ph = (uint32_t)(cc / p.slab_stages) & 1u;
-        mbar_wait(empty_slab + 8 * s, ph ^ 1u);
-        mbar_expect_tx(full_slab + 8 * s, slab_bytes);
-        for (int i = 0; i < p.slab_boxes; ++i)
-          tma_load_3d(slab0 + s * p.slab_stage_bytes + i * p.slab_box_rows * ROW_BYTES, &p.mx, full_slab + 8 * s,
-                      cc * KC, t0 - p.pad_left + i * p.slab_box_rows, b);
-        for (int j = 0; j < p.k; ++j, ++wit) {
-          const int ws = wit % p.w_stages;
-          const uint32_t wph = (uint32_t)(wit / p.w_stages) & 1u;
-          mbar_wait(empty_w + 8 * ws, wph ^ 1u);
-          mbar_expect_tx(full_w + 8 * ws, w_bytes);
-          for (int i = 0; i < p.w_boxes; ++i)
-            tma_load_2d(w0 + ws * p.w_stage_bytes + i * p.w_box_rows * ROW_BYTES, &p.mw, full_w + 8 * ws,
-                        j * p.cin + cc * KC, n0 + i * p.w_box_rows);
+      uint32_t sit = 0, wit = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int gi = tile % p.ngroups;
+        const int rest = tile / p.ngroups;
+        const int tb = rest % p.ntb, b = rest / p.ntb;
+        const int t0 = tb * N;
+        const int gs = p.gsize[gi];
+        for (int cc = 0; cc < n_cchunks; ++cc, ++sit) {
+          const uint32_t s = sit % p.slab_stages;
+          const uint32_t ph = (sit / p.slab_stages) & 1u;
+          mbar_wait(empty_slab + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full_slab + 8 * s, slab_bytes);
+          for (int i = 0; i < p.slab_boxes; ++i)
+            tma_load_3d(slab0 + s * p.slab_stage_bytes + i * p.slab_box_rows * ROW_BYTES, &p.mx, full_slab + 8 * s,
+                        cc * KC, t0 - p.pad_left + i * p.slab_box_rows, b);
+          for (int j = 0; j < p.k; ++j, ++wit) {
+            const uint32_t ws = wit % p.w_stages;
+            const uint32_t wph = (wit / p.w_stages) & 1u;
+            mbar_wait(empty_w + 8 * ws, wph ^ 1u);
+            mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
+            for (int ci = 0; ci < gs; ++ci)
+              tma_load_2d(w0 + ws * p.w_stage_bytes + ci * CHUNK_BYTES, &p.mw, full_w + 8 * ws,
+                          j * p.cin + cc * KC, p.row0[gi][ci]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.nchunk >> 3) << 17) |
-                             ((uint32_t)(TILE_M >> 4) << 24);
-      int wit = 0;
-      for (int cc = 0; cc < n_cchunks; ++cc) {
-        const int s = cc % p.slab_stages;
-        const uint32_t ph = (uint32_t)(cc / p.slab_stages) & 1u;
-        mbar_wait(full_slab + 8 * s, ph);
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(CHUNK_M >> 4) << 24);
+      uint32_t sit = 0, wit = 0, ait = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ait) {
+        const int gi = tile % p.ngroups;
+        const int gs = p.gsize[gi];
+        const uint32_t buf = ait & 1u;
+        mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator set
         tc_fence_after();
-        const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-        for (int j = 0; j < p.k; ++j, ++wit) {
-          const int ws = wit % p.w_stages;
-          const uint32_t wph = (uint32_t)(wit / p.w_stages) & 1u;
-          mbar_wait(full_w + 8 * ws, wph);
+        const uint32_t dbase = tmem_base + buf * ACC_COLS;
+        for (int cc = 0; cc < n_cchunks; ++cc, ++sit) {
+          const uint32_t s = sit % p.slab_stages;
+          const uint32_t ph = (sit / p.slab_stages) & 1u;
+          mbar_wait(full_slab + 8 * s, ph);
           tc_fence_after();
-          const uint32_t wst = w0 + ws * p.w_stage_bytes;
-          const uint32_t first = (cc | j) == 0 ? 0u : 1u;
-          for (int m = 0; m < p.mt; ++m) {
-            const uint32_t a_row = slab + (uint32_t)(m * TILE_M + j * p.dil) * ROW_BYTES;
-            for (int ns = 0; ns < p.nsplit; ++ns) {
-              const uint32_t b_row = wst + (uint32_t)(ns * p.nchunk) * ROW_BYTES;
-              const uint32_t d = tmem_base + (uint32_t)(m * p.nc + ns * p.nchunk);
+          const uint32_t slab = slab0 + s * p.slab_stage_bytes;
+          for (int j = 0; j < p.k; ++j, ++wit) {
+            const uint32_t ws = wit % p.w_stages;
+            const uint32_t wph = (wit / p.w_stages) & 1u;
+            mbar_wait(full_w + 8 * ws, wph);
+            tc_fence_after();
+            const uint32_t wst = w0 + ws * p.w_stage_bytes;
+            const uint32_t first = (cc | j) == 0 ? 0u : 1u;
+            const uint32_t b_row = slab + (uint32_t)(j * p.dil) * ROW_BYTES;
+            for (int ci = 0; ci < gs; ++ci) {
+              const uint32_t a_row = wst + (uint32_t)ci * CHUNK_BYTES;
+              const uint32_t d = dbase + (uint32_t)(ci * N);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma<OPF>(d, smem_desc(a_row + ks * 32, p.desc_mode), smem_desc(b_row + ks * 32, p.desc_mode), idesc,
-                          ks == 0 ? first : 1u);
+                umma<OPF>(d, smem_desc(a_row + ks * 32), smem_desc(b_row + ks * 32), idesc, ks == 0 ? first : 1u);
             }
+            tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
           }
-          tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
+          tc_commit(empty_slab + 8 * s);
         }
-        tc_commit(empty_slab + 8 * s);
+        tc_commit(tmem_full + 8 * buf);
       }
-      tc_commit(tmem_full);
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    for (int m = 0; m < p.mt; ++m) {
-      const int t = t0 + m * TILE_M + q * 32 + lane;
-      const bool live = t < p.ep.out_rows;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * p.nc);
+    const int h = (warp - 2) >> 2;                 // which half of the tile's frames
+    const int nblk = N >> 5;
+    const int col_begin = h == 0 ? 0 : ((nblk + 1) >> 1) << 5;
+    const int col_end = h == 0 ? ((nblk + 1) >> 1) << 5 : N;
+    const int lic = q * 32 + lane;                 // lane within the 128-channel chunk
+    uint32_t ait = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ait) {
+      const int gi = tile % p.ngroups;
+      const int rest = tile / p.ngroups;
+      const int tb = rest % p.ntb, b = rest / p.ntb;
+      const int t0 = tb * N;
+      const int gs = p.gsize[gi];
+      const uint32_t buf = ait & 1u;
+      mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
       if constexpr (EPI == QVC_EPI_LINEAR) {
-        for (int c = 0; c < p.nc; c += 16) {
-          float v[16];
-          tmem_ld16(trow + c, v);
-          if (live) {
-            epi_linear<OPF, 8>(p.ep, b, t, n0 + c, v);
-            epi_linear<OPF, 8>(p.ep, b, t, n0 + c + 8, v + 8);
+        for (int ci = 0; ci < gs; ++ci) {
+          const int nvalid = p.valid[gi][ci];
+          if (q * 32 >= nvalid) continue;                        // warp-uniform: no live channel in this quarter
+          const int n_w = p.row0[gi][ci] + q * 32;
+          const int n = n_w + lane;
+          const int s = (p.ep.nseg > 1 && n_w >= p.ep.seg[1].col0) ? 1 : 0;
+          const EpiSeg& sg = p.ep.seg[s];
+          const int c = n - sg.col0;
+          const bool ok = lic < nvalid && c >= 0 && c < sg.ncols;
+          const float bias_v = (p.ep.bias && ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
+          for (int col = col_begin; col < col_end; col += 32) {
+            const int t = t0 + col;
+            const int nv = min(32, p.ep.out_rows - t);
+            if (nv <= 0) break;
+            epi_linear_cols<OPF>(sg, b, t, nv, ok ? c : 0, ok, bias_v, tbase + (uint32_t)(ci * N + col));
           }
         }
       } else {
-        const int half = p.nc >> 1;
-        for (int c = 0; c < half; c += 8) {
-          float lo[8], hi[8];
-          tmem_ld8(trow + c, lo);
-          tmem_ld8(trow + half + c, hi);
-          if (live) {
-            if constexpr (EPI == QVC_EPI_GATE) epi_gate<OPF, 8>(p.ep, b, t, c, lo, hi);
-            else                               epi_sample<OPF, 8>(p.ep, b, t, c, lo, hi);
+        const int nlo = gs >> 1;
+        for (int ci = 0; ci < nlo; ++ci) {
+          const int nvalid = p.valid[gi][ci];
+          if (q * 32 >= nvalid) continue;
+          const int n = p.row0[gi][ci] + lic;
+          const bool ok = lic < nvalid;
+          const float* bias = p.ep.bias + (int64_t)b * p.ep.bias_bs;
+          const float bias_lo = ok ? bias[n] : 0.f, bias_hi = ok ? bias[p.ep.half + n] : 0.f;
+          for (int col = col_begin; col < col_end; col += 32) {
+            const int t = t0 + col;
+            const int nv = min(32, p.ep.out_rows - t);
+            if (nv <= 0) break;
+            const uint32_t ta_lo = tbase + (uint32_t)(ci * N + col), ta_hi = tbase + (uint32_t)((ci + nlo) * N + col);
+            if constexpr (EPI == QVC_EPI_GATE) epi_gate_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, bias_lo, bias_hi, ta_lo, ta_hi);
+            else                               epi_sample_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, bias_lo, bias_hi, ta_lo, ta_hi);
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
     }
   }
 
@@ -281,7 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
   }
 }
 
@@ -305,16 +495,23 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int desc_mode_from_env() {
-  static int mode = [] {
-    const char* e = getenv("QVC_TC_DESC_MODE");
-    return e ? atoi(e) : 0;
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    return v;
   }();
-  return mode;
+  return n;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 template <int OPF, int EPI>
-int launch_variant(const TcParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
@@ -342,60 +539,70 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   TcParams p{};
   QVC_PROPAGATE(build_epi_params(a, &p.ep));
   p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
-  p.desc_mode = desc_mode_from_env();
 
-  // ---- tile shape ----
+  // ---- output-channel chunks (TMEM lanes) and groups ----
   const bool paired = a.epilogue != QVC_EPI_LINEAR;
-  int nc;
-  if (a.cout <= 512) nc = a.cout;
-  else if (a.cout % 256 == 0) nc = 256;
-  else if (a.cout % 128 == 0) nc = 128;
-  else { set_error("conv1d(tcgen05): cout %d unsupported", a.cout); return QVC_ERR_UNSUPPORTED; }
-  QVC_REQUIRE(!paired || nc == a.cout, "conv1d(tcgen05): paired epilogue needs cout <= 512");
-  p.nc = nc;
-  p.nsplit = nc <= 256 ? 1 : 2;
-  p.nchunk = nc / p.nsplit;
-  QVC_REQUIRE(p.nchunk % 16 == 0 && p.nchunk <= 256, "conv1d(tcgen05): MMA N %d invalid", p.nchunk);
-  const int halo = (a.k - 1) * a.dil;
-  const int grid_y = a.cout / nc;
-
-  // filter stage
-  p.w_boxes = nc <= 256 ? 1 : 2;
-  p.w_box_rows = nc / p.w_boxes;
-  p.w_stage_bytes = (uint32_t)nc * ROW_BYTES;
-
-  // accumulator tiles per CTA: as many as TMEM / shared memory allow, but keep the grid >= ~2 waves
-  int mt = 512 / nc;
-  if (mt > 4) mt = 4;
-  if (mt < 1) mt = 1;
-  const char* mt_env = getenv("QVC_TC_MT");
-  if (mt_env && atoi(mt_env) >= 1 && atoi(mt_env) <= mt) mt = atoi(mt_env);
-  while (mt > 1) {
-    const long tiles = (long)((a.out_rows + mt * TILE_M - 1) / (mt * TILE_M)) * grid_y * a.batch;
-    if (tiles >= 2 * 148 || a.out_rows > (mt / 2) * TILE_M && tiles >= 148) break;
-    mt >>= 1;
+  const int rows32 = ((a.out_rows + 31) / 32) * 32;
+  int g;                                           // chunks per tile
+  if (paired) {
+    const int half = a.cout / 2;
+    const int nlo = (half + CHUNK_M - 1) / CHUNK_M;
+    QVC_REQUIRE(2 * nlo <= MAXG, "conv1d(tcgen05): paired epilogue supports cout <= %d (got %d)", MAXG * CHUNK_M, a.cout);
+    g = 2 * nlo;
+    p.ngroups = 1;
+    p.gsize[0] = g;
+    for (int i = 0; i < nlo; ++i) {
+      p.row0[0][i] = i * CHUNK_M;            p.valid[0][i] = half - i * CHUNK_M < CHUNK_M ? half - i * CHUNK_M : CHUNK_M;
+      p.row0[0][nlo + i] = half + i * CHUNK_M; p.valid[0][nlo + i] = p.valid[0][i];
+    }
+  } else {
+    if (a.nseg == 2)
+      QVC_REQUIRE(a.seg[1].col0 % 32 == 0 && a.seg[0].col0 % 32 == 0 && a.seg[0].ncols % 32 == 0,
+                  "conv1d(tcgen05): segment boundaries must be multiples of 32 columns");
+    const int chunks = (a.cout + CHUNK_M - 1) / CHUNK_M;
+    g = chunks >= 2 ? 2 : 1;
+    if (rows32 <= 64 && chunks >= 4) g = 4;       // short series: more channels per tile instead of frames
+    const int g_env = env_int("QVC_TC_G", 0);
+    if (g_env >= 1 && g_env <= MAXG && g_env <= chunks) g = g_env;
+    p.ngroups = (chunks + g - 1) / g;
+    QVC_REQUIRE(p.ngroups <= MAXGROUPS, "conv1d(tcgen05): cout %d needs more than %d channel groups", a.cout, MAXGROUPS);
+    for (int gi = 0; gi < p.ngroups; ++gi) {
+      const int first = gi * g;
+      p.gsize[gi] = chunks - first < g ? chunks - first : g;
+      for (int ci = 0; ci < p.gsize[gi]; ++ci) {
+        const int r0 = (first + ci) * CHUNK_M;
+        p.row0[gi][ci] = r0;
+        p.valid[gi][ci] = a.cout - r0 < CHUNK_M ? a.cout - r0 : CHUNK_M;
+      }
+    }
   }
-  int slab_stages = 2, w_stages = 4;
-  for (;;) {
-    const int rows = mt * TILE_M + halo;
-    p.slab_boxes = (rows + 255) / 256;
-    p.slab_box_rows = (((rows + p.slab_boxes - 1) / p.slab_boxes) + 7) & ~7;
-    p.slab_stage_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
-    const size_t need = (size_t)slab_stages * p.slab_stage_bytes + (size_t)w_stages * p.w_stage_bytes + 1024 + 256;
-    if (need <= (size_t)MAX_SMEM) break;
-    if (w_stages > 2) { --w_stages; continue; }
-    if (mt > 1) { mt >>= 1; w_stages = 4; continue; }
-    set_error("conv1d(tcgen05): tile does not fit shared memory (k=%d dil=%d nc=%d)", a.k, a.dil, nc);
+  int ntime = (ACC_COLS / g) & ~31;
+  if (rows32 < ntime) ntime = rows32;
+  const int n_env = env_int("QVC_TC_N", 0);
+  if (n_env >= 32 && n_env % 32 == 0 && n_env <= ntime) ntime = n_env;
+  p.ntime = ntime;
+  p.ntb = (a.out_rows + ntime - 1) / ntime;
+  p.ntiles = a.batch * p.ntb * p.ngroups;
+
+  // ---- shared-memory pipeline ----
+  const int halo = (a.k - 1) * a.dil;
+  const int rows = ntime + halo;
+  p.slab_boxes = (rows + 255) / 256;
+  p.slab_box_rows = (((rows + p.slab_boxes - 1) / p.slab_boxes) + 7) & ~7;
+  QVC_REQUIRE(p.slab_box_rows <= 256, "conv1d(tcgen05): slab box too tall");
+  p.slab_stage_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
+  p.w_stage_bytes = (uint32_t)g * CHUNK_BYTES;
+  static const int stage_options[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {2, 2}, {1, 2}};
+  size_t smem = 0;
+  bool fits = false;
+  for (const auto& opt : stage_options) {
+    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256;
+    if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
+  }
+  if (!fits) {
+    set_error("conv1d(tcgen05): tile does not fit shared memory (k=%d dil=%d cout=%d)", a.k, a.dil, a.cout);
     return QVC_ERR_UNSUPPORTED;
   }
-  QVC_REQUIRE(p.slab_box_rows <= 256, "conv1d(tcgen05): slab box too tall");
-  p.mt = mt;
-  p.slab_stages = slab_stages;
-  p.w_stages = w_stages;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(mt * nc)) cols <<= 1;
-  p.tmem_cols = cols;
-  const size_t smem = (size_t)slab_stages * p.slab_stage_bytes + (size_t)w_stages * p.w_stage_bytes + 1024 + 256;
 
   // ---- tensor maps ----
   const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -412,14 +619,16 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)a.k * a.cin, (cuuint64_t)a.cout};
     cuuint64_t strides[1] = {(cuuint64_t)a.k * a.cin * esize};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)p.w_box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)CHUNK_M};
     cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&p.mw, dt, 2, const_cast<void*>(a.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
   }
 
-  dim3 grid((a.out_rows + mt * TILE_M - 1) / (mt * TILE_M), grid_y, a.batch);
+  int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+  const int grid_env = env_int("QVC_TC_GRID", 0);
+  if (grid_env >= 1 && grid_env < grid) grid = grid_env;
 #define QVC_TC_DISPATCH(OPF)                                                                         \
   switch (a.epilogue) {                                                                              \
     case QVC_EPI_LINEAR: return launch_variant<OPF, QVC_EPI_LINEAR>(p, grid, smem, stream);          \
