@@ -545,15 +545,17 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   const int rows32 = ((a.out_rows + 31) / 32) * 32;
   int g;                                           // chunks per tile
   if (paired) {
+    // group i = { lo chunk i, hi chunk i }: both members of a gate pair on the same TMEM lane, two
+    // chunks per tile so that a tile spans 128 frames (weights re-streamed per 128 frames, not 64)
     const int half = a.cout / 2;
     const int nlo = (half + CHUNK_M - 1) / CHUNK_M;
-    QVC_REQUIRE(2 * nlo <= MAXG, "conv1d(tcgen05): paired epilogue supports cout <= %d (got %d)", MAXG * CHUNK_M, a.cout);
-    g = 2 * nlo;
-    p.ngroups = 1;
-    p.gsize[0] = g;
+    QVC_REQUIRE(nlo <= MAXGROUPS, "conv1d(tcgen05): paired epilogue supports cout <= %d (got %d)", 2 * MAXGROUPS * CHUNK_M, a.cout);
+    g = 2;
+    p.ngroups = nlo;
     for (int i = 0; i < nlo; ++i) {
-      p.row0[0][i] = i * CHUNK_M;            p.valid[0][i] = half - i * CHUNK_M < CHUNK_M ? half - i * CHUNK_M : CHUNK_M;
-      p.row0[0][nlo + i] = half + i * CHUNK_M; p.valid[0][nlo + i] = p.valid[0][i];
+      p.gsize[i] = 2;
+      p.row0[i][0] = i * CHUNK_M;        p.valid[i][0] = half - i * CHUNK_M < CHUNK_M ? half - i * CHUNK_M : CHUNK_M;
+      p.row0[i][1] = half + i * CHUNK_M; p.valid[i][1] = p.valid[i][0];
     }
   } else {
     if (a.nseg == 2)

@@ -276,6 +276,32 @@ int run_decoder(const Ctx& c, const Buffers& bf, const Shapes& s, const void* zO
   return QVC_OK;
 }
 
+// Fork / join helper: the speaker encoder (384 strictly sequential LSTM cell steps on one 8-CTA
+// cluster, ~1.7 ms) depends only on `mel`, so it runs on a side stream beside the prior encoder and
+// joins before the first layer that needs the conditioning vectors (the flow).  One side stream and
+// event pair per host thread and device; works under stream capture (fork and join are event edges).
+struct SideStream {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+int side_stream(SideStream** out) {
+  static thread_local SideStream pool[16];
+  int dev = 0;
+  QVC_CHECK_CUDA(cudaGetDevice(&dev));
+  QVC_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);
+  SideStream& s = pool[dev];
+  if (s.dev != dev) {
+    QVC_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    QVC_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    QVC_CHECK_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    s.dev = dev;
+  }
+  *out = &s;
+  return QVC_OK;
+}
+
 int check_model(const qvc_model* m) {
   QVC_REQUIRE(m != nullptr, "null model");
   QVC_REQUIRE(m->abi_version == QVC_ABI_VERSION, "model built for ABI %d, library is %d", m->abi_version, QVC_ABI_VERSION);
@@ -339,15 +365,23 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
   QVC_PROPAGATE(qvc_to_series_major(unit, bf.unitO, B, UNIT_CH, T, m->opformat, stream));
   QVC_PROPAGATE(qvc_to_series_major(noise, bf.noiseT, B, HID, T, QVC_OPF_F32, stream));
 
-  // speaker embedding and the per-utterance bias vectors derived from it (models.py:635)
+  // speaker embedding and the per-utterance bias vectors derived from it (models.py:635), on the
+  // side stream when the encoder has to run
   const float* g = g_in;
+  SideStream* side = nullptr;
+  cudaStream_t gst = c.st;
   if (with_spk) {
-    QVC_PROPAGATE(qvc_spk_embed(&m->spk, mel, mel_batch, mel_frames, bf.g, bf.spk_ws, bf.spk_ws_bytes, stream));
+    QVC_PROPAGATE(side_stream(&side));
+    QVC_CHECK_CUDA(cudaEventRecord(side->fork, c.st));
+    QVC_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    gst = side->stream;
+    QVC_PROPAGATE(qvc_spk_embed(&m->spk, mel, mel_batch, mel_frames, bf.g, bf.spk_ws, bf.spk_ws_bytes, (qvc_stream_t)gst));
     g = bf.g;
   }
   if (taps && taps->g)
-    QVC_CHECK_CUDA(cudaMemcpyAsync(taps->g, g, (size_t)n_embed * GIN * 4, cudaMemcpyDeviceToDevice, c.st));
-  QVC_PROPAGATE(cond_vectors(m->cond_w, m->cond_b, g, n_embed, m->cond_rows, bf.condvec, c.st));
+    QVC_CHECK_CUDA(cudaMemcpyAsync(taps->g, g, (size_t)n_embed * GIN * 4, cudaMemcpyDeviceToDevice, gst));
+  QVC_PROPAGATE(cond_vectors(m->cond_w, m->cond_b, g, n_embed, m->cond_rows, bf.condvec, gst));
+  if (side) QVC_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
   const int64_t cond_bs = n_embed > 1 ? m->cond_rows : 0;
 
   // prior encoder enc_p (models.py:75-95)
@@ -373,6 +407,7 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
   }
 
   // flow, reverse direction, Flips folded into the weights (models.py:39-51, modules.py:165-224)
+  if (side) QVC_CHECK_CUDA(cudaStreamWaitEvent(c.st, side->join, 0));      // conditioning vectors ready
   for (int cpl = 0; cpl < 4; ++cpl) {
     const int lb = L_FLOW + 10 * cpl;
     qvc_conv_args a = layer_args(c, lb, tens(bf.zO, bs, HID), B, T, T);
