@@ -40,7 +40,7 @@ constexpr int MAX_SMEM = 232448;          // 227 KB
 constexpr int NTHREADS = 320;
 constexpr int N_EPI_WARPS = 8;
 constexpr int MAXG = 4;                   // output-channel chunks per tile
-constexpr int MAXGROUPS = 8;              // output-channel groups per layer
+constexpr int MAXGROUPS = 10;              // output-channel groups per layer
 constexpr int ACC_COLS = 256;             // TMEM columns per accumulator set
 
 struct alignas(64) TcParams {
@@ -56,6 +56,7 @@ struct alignas(64) TcParams {
   int32_t slab_boxes, slab_box_rows;       // slab = slab_boxes TMA boxes of slab_box_rows frames
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes, w_stage_bytes;
+  int32_t debug;                           // diagnostics only (QVC_TC_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue I/O
   EpiParams ep;
 };
 
@@ -103,6 +104,18 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// One lane of a converged warp (the pattern ptxas recognises: no per-instruction election loop around
+// the warp-level tcgen05 instructions, unlike `if (lane == 0)`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 template <int OPF>
@@ -337,73 +350,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mx) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
       const uint32_t slab_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
-      uint32_t sit = 0, wit = 0;
+      // stage indices / phase parities are carried incrementally: a runtime integer division per K block
+      // on this single thread (I2F / MUFU.RCP chains) cost more than the MMAs it feeds
+      uint32_t s = 0, ph = 0, ws = 0, wph = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int gi = tile % p.ngroups;
         const int rest = tile / p.ngroups;
         const int tb = rest % p.ntb, b = rest / p.ntb;
         const int t0 = tb * N;
         const int gs = p.gsize[gi];
-        for (int cc = 0; cc < n_cchunks; ++cc, ++sit) {
-          const uint32_t s = sit % p.slab_stages;
-          const uint32_t ph = (sit / p.slab_stages) & 1u;
+        for (int cc = 0; cc < n_cchunks; ++cc) {
           mbar_wait(empty_slab + 8 * s, ph ^ 1u);
-          mbar_expect_tx(full_slab + 8 * s, slab_bytes);
-          for (int i = 0; i < p.slab_boxes; ++i)
+          if (p.debug & 1) mbar_arrive(full_slab + 8 * s);
+          else             mbar_expect_tx(full_slab + 8 * s, slab_bytes);
+          for (int i = 0; i < p.slab_boxes && !(p.debug & 1); ++i)
             tma_load_3d(slab0 + s * p.slab_stage_bytes + i * p.slab_box_rows * ROW_BYTES, &p.mx, full_slab + 8 * s,
                         cc * KC, t0 - p.pad_left + i * p.slab_box_rows, b);
-          for (int j = 0; j < p.k; ++j, ++wit) {
-            const uint32_t ws = wit % p.w_stages;
-            const uint32_t wph = (wit / p.w_stages) & 1u;
+          if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
+          for (int j = 0; j < p.k; ++j) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
-            mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
-            for (int ci = 0; ci < gs; ++ci)
+            if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
+            else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
+            for (int ci = 0; ci < gs && !(p.debug & 1); ++ci)
               tma_load_2d(w0 + ws * p.w_stage_bytes + ci * CHUNK_BYTES, &p.mw, full_w + 8 * ws,
                           j * p.cin + cc * KC, p.row0[gi][ci]);
+            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(N >> 3) << 17) |
-                             ((uint32_t)(CHUNK_M >> 4) << 24);
-      uint32_t sit = 0, wit = 0, ait = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ait) {
-        const int gi = tile % p.ngroups;
-        const int gs = p.gsize[gi];
-        const uint32_t buf = ait & 1u;
-        mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator set
-        tc_fence_after();
-        const uint32_t dbase = tmem_base + buf * ACC_COLS;
-        for (int cc = 0; cc < n_cchunks; ++cc, ++sit) {
-          const uint32_t s = sit % p.slab_stages;
-          const uint32_t ph = (sit / p.slab_stages) & 1u;
-          mbar_wait(full_slab + 8 * s, ph);
+    // The whole warp walks the pipeline (waits are warp-wide); one elected lane issues the MMAs and commits.
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(N >> 3) << 17) |
+                           ((uint32_t)(CHUNK_M >> 4) << 24);
+    const uint64_t desc_hi = smem_desc(0);         // everything but the start address
+    // Stage indices / phase parities are carried incrementally (no runtime division on this path).
+    // Measured on B200 (scripts/conv_bench.py with QVC_TC_DEBUG): this loop is not the limiter -- an
+    // M = 128, N = 256 MMA with both operands in shared memory takes ~190 cycles instead of 128, i.e. the
+    // 12 KB of operand reads per MMA run at ~64 B/cycle; batching several K blocks per trip changes nothing.
+    uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ait) {
+      const int gi = tile % p.ngroups;
+      const int gs = (p.debug & 2) ? 0 : p.gsize[gi];
+      const uint32_t buf = ait & 1u;
+      mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator set
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + buf * ACC_COLS;
+      for (int cc = 0; cc < n_cchunks; ++cc) {
+        mbar_wait(full_slab + 8 * s, ph);
+        const uint32_t slab = slab0 + s * p.slab_stage_bytes;
+        for (int j = 0; j < p.k; ++j) {
+          mbar_wait(full_w + 8 * ws, wph);
           tc_fence_after();
-          const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-          for (int j = 0; j < p.k; ++j, ++wit) {
-            const uint32_t ws = wit % p.w_stages;
-            const uint32_t wph = (wit / p.w_stages) & 1u;
-            mbar_wait(full_w + 8 * ws, wph);
-            tc_fence_after();
-            const uint32_t wst = w0 + ws * p.w_stage_bytes;
-            const uint32_t first = (cc | j) == 0 ? 0u : 1u;
-            const uint32_t b_row = slab + (uint32_t)(j * p.dil) * ROW_BYTES;
+          const uint32_t wst = w0 + ws * p.w_stage_bytes;
+          const uint32_t first = (cc | j) == 0 ? 0u : 1u;
+          const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
             for (int ci = 0; ci < gs; ++ci) {
-              const uint32_t a_row = wst + (uint32_t)ci * CHUNK_BYTES;
+              const uint64_t adesc = desc_hi | (uint64_t)(((wst + (uint32_t)ci * CHUNK_BYTES) & 0x3FFFFu) >> 4);
               const uint32_t d = dbase + (uint32_t)(ci * N);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma<OPF>(d, smem_desc(a_row + ks * 32), smem_desc(b_row + ks * 32), idesc, ks == 0 ? first : 1u);
+              for (int ks = 0; ks < 4; ++ks)      // +32 bytes per K step = +2 in the (addr >> 4) field
+                umma<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
             }
             tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
+            if (j == p.k - 1) tc_commit(empty_slab + 8 * s);
           }
-          tc_commit(empty_slab + 8 * s);
+          __syncwarp();
+          if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
         }
-        tc_commit(tmem_full + 8 * buf);
+        if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
       }
+      if (elect_one()) tc_commit(tmem_full + 8 * buf);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -437,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           const float bias_v = (p.ep.bias && ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
           for (int col = col_begin; col < col_end; col += 32) {
             const int t = t0 + col;
-            const int nv = min(32, p.ep.out_rows - t);
+            const int nv = (p.debug & 4) ? 0 : min(32, p.ep.out_rows - t);
             if (nv <= 0) break;
             epi_linear_cols<OPF>(sg, b, t, nv, ok ? c : 0, ok, bias_v, tbase + (uint32_t)(ci * N + col));
           }
@@ -539,6 +559,7 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   TcParams p{};
   QVC_PROPAGATE(build_epi_params(a, &p.ep));
   p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
+  p.debug = env_int("QVC_TC_DEBUG", 0);
 
   // ---- output-channel chunks (TMEM lanes) and groups ----
   const bool paired = a.epilogue != QVC_EPI_LINEAR;
@@ -562,8 +583,12 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
       QVC_REQUIRE(a.seg[1].col0 % 32 == 0 && a.seg[0].col0 % 32 == 0 && a.seg[0].ncols % 32 == 0,
                   "conv1d(tcgen05): segment boundaries must be multiples of 32 columns");
     const int chunks = (a.cout + CHUNK_M - 1) / CHUNK_M;
-    g = chunks >= 2 ? 2 : 1;
-    if (rows32 <= 64 && chunks >= 4) g = 4;       // short series: more channels per tile instead of frames
+    // One chunk x 256 frames per tile: measured on B200 (scripts/conv_bench.py) an N = 256 MMA costs about
+    // the same issue slot as an N = 128 one, so wide-N tiles win even though the slab is re-read once per
+    // chunk.  Short series put more chunks on a tile instead of frames.
+    g = 1;
+    if (rows32 <= 128 && chunks >= 2) g = 2;
+    if (rows32 <= 64 && chunks >= 4) g = 4;
     const int g_env = env_int("QVC_TC_G", 0);
     if (g_env >= 1 && g_env <= MAXG && g_env <= chunks) g = g_env;
     p.ngroups = (chunks + g - 1) / g;
@@ -594,12 +619,18 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   QVC_REQUIRE(p.slab_box_rows <= 256, "conv1d(tcgen05): slab box too tall");
   p.slab_stage_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
   p.w_stage_bytes = (uint32_t)g * CHUNK_BYTES;
-  static const int stage_options[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {2, 2}, {1, 2}};
+  static const int stage_options[][2] = {{3, 6}, {3, 4}, {2, 4}, {2, 3}, {2, 2}, {1, 2}};
   size_t smem = 0;
   bool fits = false;
+  const int ss_env = env_int("QVC_TC_SS", 0), ws_env = env_int("QVC_TC_WS", 0);
+  if (ss_env >= 1 && ws_env >= 1 && ss_env <= 8 && ws_env <= 12 && ws_env >= 2) {
+    smem = (size_t)ss_env * p.slab_stage_bytes + (size_t)ws_env * p.w_stage_bytes + 1024 + 256;
+    if (smem <= (size_t)MAX_SMEM) { p.slab_stages = ss_env; p.w_stages = ws_env; fits = true; }
+  }
   for (const auto& opt : stage_options) {
+    if (fits) break;
     smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256;
-    if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
+    if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; }
   }
   if (!fits) {
     set_error("conv1d(tcgen05): tile does not fit shared memory (k=%d dil=%d cout=%d)", a.k, a.dil, a.cout);
