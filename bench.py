@@ -257,18 +257,42 @@ def run_ours(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel class (tcgen05 series convolutions: 99.9 % of the FLOPs) ----
-    flops = B * T * FLOP_PER_FRAME + n_windows(TM) * FLOP_PER_WINDOW
-    achieved = flops / (ms * 1e-3) / 1e12
+    # ---- roofline of the dominant kernel: conv_tc_kernel, the tcgen05 series convolution (99.9 % of the
+    # FLOPs, 113 of the 127 launches of a step).  Its launches are timed live with CUDA events on the
+    # launching stream (qvc_profile, include/qvc_b200.h) over `prof_steps` further steps of the same
+    # workload; achieved = algorithmic conv FLOPs of a step / summed duration of its conv launches.
+    import ctypes as C
+    lib = capi.load()
+    prof_steps = 3
+    flush.zero_()
+    torch.cuda.synchronize()
+    capi.check(lib.qvc_profile(1), "qvc_profile")
+    for _ in range(prof_steps):
+        net.infer(unit, mel, noise=noise)
+    torch.cuda.synchronize()
+    capi.check(lib.qvc_profile(0), "qvc_profile")
+    conv_ms, conv_n = C.c_double(0.0), C.c_uint64(0)
+    capi.check(lib.qvc_profile_read(C.byref(conv_ms), C.byref(conv_n)), "qvc_profile_read")
+    conv_ms_step = conv_ms.value / prof_steps
+    conv_launches = conv_n.value // prof_steps
+    conv_flops = B * T * FLOP_PER_FRAME
+    flops = conv_flops + n_windows(TM) * FLOP_PER_WINDOW
+    achieved = conv_flops / (conv_ms_step * 1e-3) / 1e12
     tf32 = args.precision != "bf16"
     peak = pk["bf16_sustained"] * (0.5 if tf32 else 1.0)
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM series convolution)",
+        "launches_per_step": int(conv_launches), "avg_launch_us": conv_ms_step * 1e3 / max(1, conv_launches),
+        "kernel_ms_per_step": conv_ms_step, "kernel_share_of_step": conv_ms_step / ms,
+        "flops_per_step": conv_flops,
         "peak_source": pk["source"] + ": bf16_tflops_sustained (kernels timed inside a long step)"
                        + (" x 0.5 -- TF32 operands run at half the bf16 tensor rate and no TF32 figure is measured" if tf32 else ""),
         "frac_of_bf16_sustained": achieved / pk["bf16_sustained"],
-        "flops_per_step": flops,
-        "note": "whole-step algorithmic FLOPs (207.2 MFLOP per unit frame per utterance + LSTM) over the CUDA-event step time",
+        "whole_step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / 1e12 / peak, "flops": flops},
+        "note": "algorithmic FLOPs (207.2 MFLOP per unit frame per utterance, SURVEY.md section 8d) over CUDA-event launch "
+                "durations summed across the kernel's launches of one step; zero-padded polyphase taps and padded output "
+                "channels are not counted as work; per-layer ncu captures: profiles/",
     }
 
     line = {
@@ -292,12 +316,10 @@ def run_ours(args, rank, local_rank, world):
     }
 
     if not args.no_extras and world == 1:
-        import ctypes as C
         # tail kernel alone: HBM roofline of the fused iSTFT / OLA / synthesis kernel
         frames_post = 20 * T + 1
         post = torch.randn(B, frames_post, 72, device=dev) * 0.3
         wave = torch.empty(B, 1, 320 * T, device=dev)
-        lib = capi.load()
         model = net._engine._ensure_model(dev)
         stream = torch.cuda.current_stream().cuda_stream
         ms_tail, _ = timed(lambda: capi.check(lib.qvc_tail(C.byref(model.tail), post.data_ptr(), 72, B, frames_post,

@@ -245,6 +245,11 @@ int qvc_abi_version(void);
 uint64_t qvc_launch_count(void);
 /* 0 when device `dev` is an sm_100 part this library has code for. */
 int qvc_check_device(int dev);
+/* Measurement aid (bench.py's roofline): while enabled, every tcgen05 series-convolution launch is
+ * bracketed by CUDA events on its own stream.  qvc_profile(1) resets and starts, qvc_profile(0) stops;
+ * qvc_profile_read synchronises the recorded events and returns their summed duration and count. */
+int qvc_profile(int enable);
+int qvc_profile_read(double* ms_total, uint64_t* launches);
 
 #ifdef __cplusplus
 }

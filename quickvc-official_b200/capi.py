@@ -94,6 +94,8 @@ SYMBOLS = {
     "qvc_abi_version": (C.c_int, []),
     "qvc_launch_count": (C.c_uint64, []),
     "qvc_check_device": (C.c_int, [C.c_int]),
+    "qvc_profile": (C.c_int, [C.c_int]),
+    "qvc_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 _lib: Optional[C.CDLL] = None

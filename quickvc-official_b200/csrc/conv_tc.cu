@@ -26,6 +26,8 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -344,6 +346,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA
+  // of this grid got here (its barrier init / TMEM allocation / tensor-map prefetch then overlap our main
+  // loop's tail); nothing above touched global memory, everything below waits for the previous grid.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -530,6 +538,33 @@ int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// ---- optional per-launch timing (qvc_profile / qvc_profile_read): CUDA events on the launching stream ----
+struct ProfState {
+  std::mutex mu;
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+};
+ProfState& prof() {
+  static ProfState st;
+  return st;
+}
+// returns the event pair to record around the next launch, or false when profiling is off
+bool prof_next(cudaEvent_t* e0, cudaEvent_t* e1) {
+  ProfState& st = prof();
+  std::lock_guard<std::mutex> lk(st.mu);
+  if (!st.on) return false;
+  if (st.used == st.ev.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    st.ev.emplace_back(a, b);
+  }
+  *e0 = st.ev[st.used].first;
+  *e1 = st.ev[st.used].second;
+  ++st.used;
+  return true;
+}
+
 template <int OPF, int EPI>
 int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_done = false;
@@ -537,7 +572,21 @@ int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream
     QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_done = true;
   }
-  conv_tc_kernel<OPF, EPI><<<grid, NTHREADS, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_int("QVC_TC_PDL", 1) ? 1 : 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool timed = prof_next(&e0, &e1);
+  if (timed) QVC_CHECK_CUDA(cudaEventRecord(e0, stream));
+  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<OPF, EPI>, p));
+  if (timed) QVC_CHECK_CUDA(cudaEventRecord(e1, stream));
   return post_launch("conv_tc_kernel");
 }
 
@@ -674,3 +723,27 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
 }
 
 }  // namespace qvc
+
+extern "C" int qvc_profile(int enable) {
+  qvc::ProfState& st = qvc::prof();
+  std::lock_guard<std::mutex> lk(st.mu);
+  st.on = enable != 0;
+  if (st.on) st.used = 0;
+  return QVC_OK;
+}
+
+extern "C" int qvc_profile_read(double* ms_total, uint64_t* launches) {
+  qvc::ProfState& st = qvc::prof();
+  std::lock_guard<std::mutex> lk(st.mu);
+  double tot = 0.0;
+  for (size_t i = 0; i < st.used; ++i) {
+    QVC_CHECK_CUDA(cudaEventSynchronize(st.ev[i].second));
+    float ms = 0.f;
+    QVC_CHECK_CUDA(cudaEventElapsedTime(&ms, st.ev[i].first, st.ev[i].second));
+    tot += ms;
+  }
+  if (ms_total) *ms_total = tot;
+  if (launches) *launches = st.used;
+  return QVC_OK;
+}
+
