@@ -184,47 +184,98 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * fast_rc
 // ----------------------------------------------------------------------------------------------
 // epilogues: one thread = one output channel, 32 consecutive frames t .. t+31 (nv of them live)
 // ----------------------------------------------------------------------------------------------
+// LINEAR epilogue on a "superblock" of up to 64 frames: the global loads of the whole superblock are
+// issued first (and, for the first superblock of a tile, before the accumulator is even complete), then the
+// two 32-frame halves are read out of TMEM, finished and stored.  Measured (scripts/micro/membench.cu): with
+// 8 warps per SM a 32-line-deep load burst per warp sustains 3.0 TB/s, a 64-line-deep one 5.3 TB/s.
+struct LinCtx {
+  const EpiSeg* sg;
+  int b, c;                 // utterance, channel within the segment
+  bool ok;                  // this lane owns a live channel
+  bool all_ok;              // ... and so does every lane of the warp
+  float bias;
+};
+
+// loads only: the residual if the segment has one, else the accumulate-into tensor (else nothing)
+__device__ __forceinline__ void lin_load(const LinCtx& k, int t, int nv, float* r) {
+  const EpiSeg& sg = *k.sg;
+  const TRef& src = sg.res.present() ? sg.res : sg.accin;
+  if (!src.present()) return;
+  const float* rp = src.at<float>(k.b, t, k.c);
+  const int ld = src.ld;
+  if (k.all_ok && nv == 64) {
+    // common case, no per-element predicate: one IMAD.WIDE + LDG per element (the predicated form costs
+    // ~9 instructions per load and made this epilogue issue-bound, profiles/r01_conv_tc_notes.md)
+#pragma unroll
+    for (int i = 0; i < 64; ++i) r[i] = rp[i * ld];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) r[i] = (k.ok && i < nv) ? rp[i * ld] : 0.f;
+  }
+}
+
 template <int OPF>
-__device__ __forceinline__ void epi_linear_cols(const EpiSeg& sg, int b, int t, int nv, int c, bool ok,
-                                                float bias_v, uint32_t taddr) {
+__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, const float* r, uint32_t taddr) {
   using OT = typename OpType<OPF>::type;
-  float v[32], r[32], a[32];
+  const EpiSeg& sg = *k.sg;
   const bool has_res = sg.res.present(), has_acc = sg.accin.present();
-  if (has_res) {
-    const float* rp = sg.res.at<float>(b, t, c);
-    const int64_t ld = sg.res.ld;
+  const float alpha = sg.alpha, beta = sg.beta, slope = sg.slope;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = (ok && i < nv) ? rp[i * ld] : 0.f;
-  }
-  if (has_acc) {
-    const float* ap = sg.accin.at<float>(b, t, c);
-    const int64_t ld = sg.accin.ld;
+  for (int h = 0; h < 2; ++h) {
+    const int th = t + 32 * h, nvh = nv - 32 * h;
+    if (nvh <= 0) break;
+    float v[32];
+    tmem_ld32(taddr + 32 * h, v);
+    tmem_wait();
+    if (has_res && has_acc) {
+      // both streams (last convolution of MRF blocks 2 and 3): the accumulate-into tensor is loaded late, 8 at a time
+      const float* ap = sg.accin.at<float>(k.b, th, k.c);
+      const int64_t ld = sg.accin.ld;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] = (ok && i < nv) ? ap[i * ld] : 0.f;
-  }
-  tmem_ld32(taddr, v);
-  tmem_wait();
-  const float alpha = sg.alpha, beta = sg.beta;
+      for (int g = 0; g < 32; g += 8) {
+        float a[8];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = alpha * (v[i] + bias_v);
-    if (has_res) x += r[i];
-    v[i] = has_acc ? fmaf(beta, x, a[i]) : beta * x;
-  }
-  if (sg.raw.present()) {
-    float* wp = sg.raw.at<float>(b, t, c);
-    const int64_t ld = sg.raw.ld;
+        for (int i = 0; i < 8; ++i) a[i] = (k.ok && g + i < nvh) ? ap[(g + i) * ld] : 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (ok && i < nv) wp[i * ld] = v[i];
-  }
-  if (sg.op.present()) {
-    OT* op = sg.op.at<OT>(b, t, c);
-    const int64_t ld = sg.op.ld;
-    const float slope = sg.slope;
+        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, r[32 * h + g + i]), a[i]);
+      }
+    } else if (has_res) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (ok && i < nv) op[i * ld] = to_operand<OPF>(leaky(v[i], slope));
+      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, r[32 * h + i]);
+    } else if (has_acc) {
+      const float ab = alpha * beta;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(ab, v[i] + k.bias, r[32 * h + i]);
+    } else {
+      const float ab = alpha * beta;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = ab * (v[i] + k.bias);
+    }
+    const bool full = k.all_ok && nvh >= 32;
+    if (sg.raw.present()) {
+      float* wp = sg.raw.at<float>(k.b, th, k.c);
+      const int ld = sg.raw.ld;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wp[i * ld] = v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (k.ok && i < nvh) wp[i * ld] = v[i];
+      }
+    }
+    if (sg.op.present()) {
+      OT* op = sg.op.at<OT>(k.b, th, k.c);
+      const int ld = sg.op.ld;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) op[i * ld] = to_operand<OPF>(fmaxf(v[i], v[i] * slope));   // leaky-relu, slope <= 1
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (k.ok && i < nvh) op[i * ld] = to_operand<OPF>(leaky(v[i], slope));
+      }
+    }
   }
 }
 
@@ -449,28 +500,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       const int t0 = tb * N;
       const int gs = p.gsize[gi];
       const uint32_t buf = ait & 1u;
-      mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
-      tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
       if constexpr (EPI == QVC_EPI_LINEAR) {
-        for (int ci = 0; ci < gs; ++ci) {
+        auto context = [&](int ci, LinCtx& k) -> bool {            // false: no live channel in this lane quarter
           const int nvalid = p.valid[gi][ci];
-          if (q * 32 >= nvalid) continue;                        // warp-uniform: no live channel in this quarter
+          if (q * 32 >= nvalid) return false;
           const int n_w = p.row0[gi][ci] + q * 32;
           const int n = n_w + lane;
-          const int s = (p.ep.nseg > 1 && n_w >= p.ep.seg[1].col0) ? 1 : 0;
-          const EpiSeg& sg = p.ep.seg[s];
-          const int c = n - sg.col0;
-          const bool ok = lic < nvalid && c >= 0 && c < sg.ncols;
-          const float bias_v = (p.ep.bias && ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
-          for (int col = col_begin; col < col_end; col += 32) {
-            const int t = t0 + col;
-            const int nv = (p.debug & 4) ? 0 : min(32, p.ep.out_rows - t);
+          k.sg = &p.ep.seg[(p.ep.nseg > 1 && n_w >= p.ep.seg[1].col0) ? 1 : 0];
+          const int c = n - k.sg->col0;
+          k.ok = lic < nvalid && c >= 0 && c < k.sg->ncols;
+          k.all_ok = __all_sync(0xffffffffu, k.ok);
+          k.c = k.ok ? c : 0;
+          k.b = b;
+          k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
+          return true;
+        };
+        auto frames_at = [&](int col) -> int {                     // live frames of the superblock starting at col
+          if (p.debug & 4) return 0;
+          const int left = min(col_end - col, p.ep.out_rows - (t0 + col));
+          return left < 64 ? left : 64;
+        };
+        float r[64];
+        LinCtx k;
+        // first superblock of the tile: loads in flight before the accumulator is complete
+        bool primed = false;
+        if (context(0, k)) {
+          const int nv = frames_at(col_begin);
+          if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
+          primed = true;
+        }
+        mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+        tc_fence_after();
+        for (int ci = 0; ci < gs; ++ci) {
+          if (!context(ci, k)) continue;
+          for (int col = col_begin; col < col_end; col += 64) {
+            const int nv = frames_at(col);
             if (nv <= 0) break;
-            epi_linear_cols<OPF>(sg, b, t, nv, ok ? c : 0, ok, bias_v, tbase + (uint32_t)(ci * N + col));
+            if (!(primed && ci == 0 && col == col_begin)) lin_load(k, t0 + col, nv, r);
+            lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)(ci * N + col));
           }
         }
       } else {
+        mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+        tc_fence_after();
         const int nlo = gs >> 1;
         for (int ci = 0; ci < nlo; ++ci) {
           const int nvalid = p.valid[gi][ci];
