@@ -279,8 +279,18 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, const
   }
 }
 
+// tanh(x) * sigmoid(y) with two ex2 and ONE rcp:  (e^{2x} - 1) / ((e^{2x} + 1) (1 + e^{-y})).
+// x is clamped to 15 (tanh(15) = 1 - 2e-13) so that e^{2x} stays finite; a huge e^{-y} makes the
+// denominator inf and the quotient 0, the correct limit.  Absolute error a few 1e-7.
+__device__ __forceinline__ float fast_gate(float x, float y) {
+  float e2x, emy;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2x) : "f"(fminf(x, 15.f) * 2.8853900817779268f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(emy) : "f"(y * -1.4426950408889634f));
+  return (e2x - 1.f) * fast_rcp((e2x + 1.f) * (1.f + emy));
+}
+
 template <int OPF>
-__device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t, int nv, int n, bool ok,
+__device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t, int nv, int n, bool ok, bool all_ok,
                                               float bias_lo, float bias_hi, uint32_t taddr_lo, uint32_t taddr_hi) {
   using OT = typename OpType<OPF>::type;
   float lo[32], hi[32];
@@ -288,21 +298,27 @@ __device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t,
   tmem_ld32(taddr_hi, hi);
   tmem_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) lo[i] = fast_tanh(lo[i] + bias_lo) * fast_sigmoid(hi[i] + bias_hi);
+  for (int i = 0; i < 32; ++i) lo[i] = fast_gate(lo[i] + bias_lo, hi[i] + bias_hi);
   const EpiSeg& sg = ep.seg[0];
+  const bool full = all_ok && nv >= 32;
   if (sg.raw.present()) {
     float* wp = sg.raw.at<float>(b, t, n);
-    const int64_t ld = sg.raw.ld;
+    const int ld = sg.raw.ld;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (ok && i < nv) wp[i * ld] = lo[i];
   }
   if (sg.op.present()) {
     OT* op = sg.op.at<OT>(b, t, n);
-    const int64_t ld = sg.op.ld;
+    const int ld = sg.op.ld;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (ok && i < nv) op[i * ld] = to_operand<OPF>(lo[i]);
+      for (int i = 0; i < 32; ++i) op[i * ld] = to_operand<OPF>(lo[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (ok && i < nv) op[i * ld] = to_operand<OPF>(lo[i]);
+    }
   }
 }
 
@@ -550,6 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           if (q * 32 >= nvalid) continue;
           const int n = p.row0[gi][ci] + lic;
           const bool ok = lic < nvalid;
+          const bool all_ok = __all_sync(0xffffffffu, ok);
           const float* bias = p.ep.bias + (int64_t)b * p.ep.bias_bs;
           const float bias_lo = ok ? bias[n] : 0.f, bias_hi = ok ? bias[p.ep.half + n] : 0.f;
           for (int col = col_begin; col < col_end; col += 32) {
@@ -557,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             const int nv = min(32, p.ep.out_rows - t);
             if (nv <= 0) break;
             const uint32_t ta_lo = tbase + (uint32_t)(ci * N + col), ta_hi = tbase + (uint32_t)((ci + nlo) * N + col);
-            if constexpr (EPI == QVC_EPI_GATE) epi_gate_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, bias_lo, bias_hi, ta_lo, ta_hi);
+            if constexpr (EPI == QVC_EPI_GATE) epi_gate_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, all_ok, bias_lo, bias_hi, ta_lo, ta_hi);
             else                               epi_sample_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, bias_lo, bias_hi, ta_lo, ta_hi);
           }
         }
