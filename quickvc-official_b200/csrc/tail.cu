@@ -79,10 +79,14 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const TailParams p) {
       float re[9], im[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        const float mag = expf(S[slot][18 * s + k]);
-        const float ph = 3.14159265358979323846f * sinf(S[slot][18 * s + 9 + k]);
+        // SFU paths (ex2 / sin / cos approx, abs error ~5e-7 after the 2*pi range reduction): the libm
+        // versions made this kernel instruction-bound at 18 % of the HBM roofline
+        const float mag = __expf(S[slot][18 * s + k]);
+        const float xp = S[slot][18 * s + 9 + k];
+        const float xr = fmaf(-6.28318530717958647692f, rintf(xp * 0.15915494309189533577f), xp);
+        const float ph = 3.14159265358979323846f * __sinf(xr);            // in [-pi, pi]
         float sn, cs;
-        sincosf(ph, &sn, &cs);
+        __sincosf(ph, &sn, &cs);
         re[k] = mag * cs;
         im[k] = mag * sn;
       }
