@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--mel-frames", type=int, default=500)
     ap.add_argument("--chunk-utts", type=int, default=0)
-    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / latency / tail side measurements")
     return ap.parse_args()
@@ -152,7 +152,7 @@ def run_reference(args, rank):
     cfg = model_cfg()
     sd = random_init_state_dict(cfg)
     budget = max(1, args.steps + args.warmup)
-    sample = max(1, min(args.cpu_sample_batch, 60 // budget))       # keep the whole run within minutes
+    sample = max(1, min(args.cpu_sample_batch, 240 // budget))      # ~1 s of CPU work per 16 utterances: whole run within minutes
     rate, sec = cpu_infer_rate(sd, sample, args.frames, args.mel_frames, args.warmup, args.steps)
     cores = os.cpu_count() or 1
     line = {
@@ -352,10 +352,10 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         sample = max(1, args.cpu_sample_batch)
-        rate, sec = cpu_infer_rate(sd, sample, T, TM, 1, 2)
+        rate, sec = cpu_infer_rate(sd, sample, T, TM, 1, 8)
         line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                 "sample": f"{sample} x {T / 50:.0f} s utterances, oracle port of the reference's PyTorch infer "
-                                          f"(fp32, torch.set_num_threads({cores})), 1 warm-up + 2 timed calls of {sec:.2f} s, "
+                                          f"(fp32, torch.set_num_threads({cores})), 1 warm-up + 8 timed calls of {sec:.2f} s, "
                                           f"CPU {cpu_model_name()}"}
     print(json.dumps(line), flush=True)
     if dist is not None:
