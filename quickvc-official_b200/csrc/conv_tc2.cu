@@ -1,0 +1,370 @@
+// conv_tc2.cu -- the series convolution of conv_tc.cu on CTA PAIRS (tcgen05 cta_group::2), for layers with
+// an even number of 128-channel output chunks (MRF-1 256 -> 256, the polyphase upsamplers, conv_pre).
+//
+// Why: measured on B200 (profiles/r01_v2_summary.md) a cta_group::1 MMA with M = 128, N = 256 and both
+// operands in shared memory runs at ~2/3 of its ideal rate -- 12 KB of operand reads per MMA at ~64 B/cycle.
+// A CTA pair issues ONE M = 256, N = 256 MMA: CTA r supplies the 128 filter rows of chunk r (A) and 128 of
+// the 256 frames (its half of B), i.e. 8 KB per CTA for the same 128 cycles, and receives the accumulator of
+// its own 128 channels x all 256 frames in its own TMEM.
+//
+//   pair tile  = (utterance, 256-frame block, group of two 128-channel chunks)
+//   CTA r      : TMA-loads frames [t0 + 128 r - pad, + 128 + halo) of every channel chunk (its slab) and the
+//                filter rows of chunk r; epilogue over its 128 channels x 256 frames (same code as conv_tc)
+//   leader (r=0): issues the MMAs; its "full" barriers collect the TMA bytes of BOTH CTAs (the peer's loads
+//                signal the leader's barrier), commits are multicast to both CTAs' "empty" / "accumulator
+//                ready" barriers; both CTAs' epilogue warps arrive on the leader's "accumulator drained" barrier.
+#include <cstdlib>
+
+#include "conv_tc_common.cuh"
+
+namespace qvc {
+
+namespace {
+
+using namespace tc;
+
+constexpr int PAIR_N = 256;               // frames per pair tile
+constexpr int HALF_N = PAIR_N / 2;        // frames whose slab rows one CTA holds
+constexpr int MAXGROUPS2 = 8;
+
+struct alignas(64) Tc2Params {
+  CUtensorMap mx;                          // x as (channel, frame, utterance)
+  CUtensorMap mw;                          // w as (tap*cin + channel, output channel)
+  int32_t cin, k, dil, pad_left;
+  int32_t ntb;                             // 256-frame blocks per utterance
+  int32_t ngroups, ntiles;                 // groups of two chunks; pair tiles
+  int32_t row0[MAXGROUPS2][2];             // filter row on lane 0 of the chunk of CTA r
+  int32_t valid[MAXGROUPS2][2];
+  int32_t slab_box_rows;                   // one TMA box per slab (128 + halo <= 256 rows)
+  int32_t slab_stages, w_stages;
+  uint32_t slab_stage_bytes;
+  EpiParams ep;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA, the bytes are counted on the barrier at `bar`
+// (a shared::cluster address -- the leader's)
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at the same offset in both CTAs once all prior MMAs of this thread have retired
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+template <int OPF>
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (OPF == QVC_OPF_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+template <int OPF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
+  constexpr int ESIZE = OPF == QVC_OPF_BF16 ? 2 : 4;
+  constexpr int KC = ROW_BYTES / ESIZE;
+  constexpr uint32_t FMT = OPF == QVC_OPF_BF16 ? 1u : 2u;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t slab0 = smem_base;
+  const uint32_t w0 = slab0 + p.slab_stages * p.slab_stage_bytes;
+  const uint32_t bar0 = w0 + p.w_stages * CHUNK_BYTES;
+  // barrier layout (same offsets in both CTAs): full_slab[SS] empty_slab[SS] full_w[WS] empty_w[WS]
+  // tmem_full[2] tmem_empty[2], then the TMEM base word.  full_* and tmem_empty are only used in the leader.
+  const uint32_t full_slab = bar0, empty_slab = full_slab + 8 * p.slab_stages;
+  const uint32_t full_w = empty_slab + 8 * p.slab_stages, empty_w = full_w + 8 * p.w_stages;
+  const uint32_t tmem_full = empty_w + 8 * p.w_stages, tmem_empty = tmem_full + 16;
+  const uint32_t tmem_slot = tmem_empty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_cchunks = p.cin / KC;
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * p.slab_stages + 2 * p.w_stages + 2; ++i) mbar_init(bar0 + 8 * i, 1);
+    mbar_init(tmem_empty, 2 * N_EPI_WARPS);
+    mbar_init(tmem_empty + 8, 2 * N_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * ACC_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // both CTAs' barriers exist before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mx) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
+      const uint32_t slab_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
+      const uint32_t lead_full_slab = map_to_cta(full_slab, 0), lead_full_w = map_to_cta(full_w, 0);
+      uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+      for (int tile = pair; tile < p.ntiles; tile += npairs) {
+        const int gi = tile % p.ngroups;
+        const int rest = tile / p.ngroups;
+        const int tb = rest % p.ntb, b = rest / p.ntb;
+        const int t0 = tb * PAIR_N + (int)rank * HALF_N;
+        const int wrow = p.row0[gi][rank];
+        for (int cc = 0; cc < n_cchunks; ++cc) {
+          mbar_wait(empty_slab + 8 * s, ph ^ 1u);
+          if (leader) mbar_expect_tx(full_slab + 8 * s, 2 * slab_bytes);       // bytes of both CTAs
+          tma2_load_3d(slab0 + s * p.slab_stage_bytes, &p.mx, lead_full_slab + 8 * s, cc * KC, t0 - p.pad_left, b);
+          if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
+          for (int j = 0; j < p.k; ++j) {
+            mbar_wait(empty_w + 8 * ws, wph ^ 1u);
+            if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * CHUNK_BYTES);
+            tma2_load_2d(w0 + ws * CHUNK_BYTES, &p.mw, lead_full_w + 8 * ws, j * p.cin + cc * KC, wrow);
+            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(PAIR_N >> 3) << 17) |
+                             ((uint32_t)((2 * CHUNK_M) >> 4) << 24);
+      const uint64_t desc_hi = smem_desc(0);
+      uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
+      for (int tile = pair; tile < p.ntiles; tile += npairs, ++ait) {
+        const uint32_t buf = ait & 1u;
+        mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this set
+        tc_fence_after();
+        const uint32_t d = tmem_base + buf * ACC_COLS;
+        for (int cc = 0; cc < n_cchunks; ++cc) {
+          mbar_wait(full_slab + 8 * s, ph);
+          const uint32_t slab = slab0 + s * p.slab_stage_bytes;
+          for (int j = 0; j < p.k; ++j) {
+            mbar_wait(full_w + 8 * ws, wph);
+            tc_fence_after();
+            const uint32_t first = (cc | j) == 0 ? 0u : 1u;
+            const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
+            const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * CHUNK_BYTES) & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma2<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              tc2_commit(empty_w + 8 * ws);
+              if (j == p.k - 1) tc2_commit(empty_slab + 8 * s);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
+          }
+          if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
+        }
+        if (elect_one()) tc2_commit(tmem_full + 8 * buf);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs): own 128 channels x 256 frames =====================
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int col_begin = h * HALF_N, col_end = col_begin + HALF_N;
+    const int lic = q * 32 + lane;
+    const uint32_t lead_tmem_empty = map_to_cta(tmem_empty, 0);
+    uint32_t ait = 0;
+    for (int tile = pair; tile < p.ntiles; tile += npairs, ++ait) {
+      const int gi = tile % p.ngroups;
+      const int rest = tile / p.ngroups;
+      const int tb = rest % p.ntb, b = rest / p.ntb;
+      const int t0 = tb * PAIR_N;
+      const uint32_t buf = ait & 1u;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+      const int nvalid = p.valid[gi][rank];
+      const bool warp_live = q * 32 < nvalid;
+      LinCtx k;
+      {
+        const int n_w = p.row0[gi][rank] + q * 32;
+        const int n = n_w + lane;
+        k.sg = &p.ep.seg[(p.ep.nseg > 1 && n_w >= p.ep.seg[1].col0) ? 1 : 0];
+        const int c = n - k.sg->col0;
+        k.ok = warp_live && lic < nvalid && c >= 0 && c < k.sg->ncols;
+        k.all_ok = __all_sync(0xffffffffu, k.ok);
+        k.c = k.ok ? c : 0;
+        k.b = b;
+        k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
+      }
+      auto frames_at = [&](int col) -> int {
+        const int left = min(col_end - col, p.ep.out_rows - (t0 + col));
+        return left < 64 ? left : 64;
+      };
+      float r[64];
+      bool primed = false;
+      if (warp_live) {
+        const int nv = frames_at(col_begin);
+        if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
+        primed = true;
+      }
+      mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+      tc_fence_after();
+      if (warp_live) {
+        for (int col = col_begin; col < col_end; col += 64) {
+          const int nv = frames_at(col);
+          if (nv <= 0) break;
+          if (!(primed && col == col_begin)) lin_load(k, t0 + col, nv, r);
+          lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)col);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer may still multicast into / arrive on this CTA's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
+  }
+}
+
+template <int OPF>
+int launch2(const Tc2Params& p, int grid, size_t smem, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<OPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_env_int("QVC_TC_PDL", 1) ? 1 : 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool timed = tc_prof_next(&e0, &e1);
+  if (timed) QVC_CHECK_CUDA(cudaEventRecord(e0, stream));
+  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<OPF>, p));
+  if (timed) QVC_CHECK_CUDA(cudaEventRecord(e1, stream));
+  return post_launch("conv_tc2_kernel");
+}
+
+}  // namespace
+
+// Returns QVC_ERR_UNSUPPORTED (without touching the error string) when the layer is not a CTA-pair case.
+int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
+  if (!tc_env_int("QVC_TC_2CTA", 1)) return QVC_ERR_UNSUPPORTED;
+  if (a.epilogue != QVC_EPI_LINEAR) return QVC_ERR_UNSUPPORTED;
+  const int chunks = (a.cout + CHUNK_M - 1) / CHUNK_M;
+  if (chunks < 2 || (chunks & 1) || chunks / 2 > MAXGROUPS2) return QVC_ERR_UNSUPPORTED;
+  if (a.out_rows <= HALF_N) return QVC_ERR_UNSUPPORTED;                       // short series: conv_tc packs chunks instead
+  const int halo = (a.k - 1) * a.dil;
+  if (HALF_N + halo > 256) return QVC_ERR_UNSUPPORTED;
+  if (a.nseg == 2 && (a.seg[1].col0 % 32 || a.seg[0].col0 % 32 || a.seg[0].ncols % 32)) return QVC_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = tc_get_encode();
+  if (!encode) return QVC_ERR_UNSUPPORTED;
+  const int esize = (int)opformat_bytes(a.opformat);
+  const int kc = ROW_BYTES / esize;
+  if (a.cin % kc) return QVC_ERR_UNSUPPORTED;
+  QVC_REQUIRE((a.x.ld * esize) % 16 == 0 && ((uintptr_t)a.x.ptr & 15) == 0 && ((uintptr_t)a.w & 15) == 0,
+              "conv1d(tcgen05): x / w must be 16-byte aligned with 16-byte row pitch");
+  QVC_REQUIRE(a.batch == 1 || (a.x.bstride * esize) % 16 == 0, "conv1d(tcgen05): utterance pitch not 16-byte aligned");
+
+  Tc2Params p{};
+  QVC_PROPAGATE(build_epi_params(a, &p.ep));
+  p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
+  p.ngroups = chunks / 2;
+  for (int gi = 0; gi < p.ngroups; ++gi)
+    for (int r = 0; r < 2; ++r) {
+      const int r0 = (2 * gi + r) * CHUNK_M;
+      p.row0[gi][r] = r0;
+      p.valid[gi][r] = a.cout - r0 < CHUNK_M ? a.cout - r0 : CHUNK_M;
+    }
+  p.ntb = (a.out_rows + PAIR_N - 1) / PAIR_N;
+  p.ntiles = a.batch * p.ntb * p.ngroups;
+  p.slab_box_rows = (HALF_N + halo + 7) & ~7;
+  p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
+  static const int stage_options[][2] = {{3, 8}, {3, 6}, {2, 6}, {2, 4}, {2, 3}, {2, 2}};
+  size_t smem = 0;
+  bool fits = false;
+  for (const auto& opt : stage_options) {
+    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * CHUNK_BYTES + 1024 + 256;
+    if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
+  }
+  if (!fits) return QVC_ERR_UNSUPPORTED;
+
+  const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.x_rows, (cuuint64_t)a.batch};
+    cuuint64_t strides[2] = {(cuuint64_t)a.x.ld * esize,
+                             (cuuint64_t)(a.batch > 1 ? a.x.bstride : (int64_t)a.x_rows * a.x.ld) * esize};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)p.slab_box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&p.mx, dt, 3, a.x.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05, pairs): cuTensorMapEncodeTiled(x) failed: %d", (int)r); return QVC_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.k * a.cin, (cuuint64_t)a.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)a.k * a.cin * esize};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)CHUNK_M};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&p.mw, dt, 2, const_cast<void*>(a.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05, pairs): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
+  }
+  int pairs = tc_sm_count() / 2;
+  if (p.ntiles < pairs) pairs = p.ntiles;
+  const int grid_env = tc_env_int("QVC_TC_GRID", 0);
+  if (grid_env >= 2 && grid_env / 2 < pairs) pairs = grid_env / 2;
+  if (a.opformat == QVC_OPF_BF16) return launch2<QVC_OPF_BF16>(p, 2 * pairs, smem, stream);
+  return launch2<QVC_OPF_TF32>(p, 2 * pairs, smem, stream);
+}
+
+}  // namespace qvc
