@@ -23,17 +23,17 @@ namespace {
 
 using namespace tc;
 
-constexpr int PAIR_N = 256;               // frames per pair tile
-constexpr int HALF_N = PAIR_N / 2;        // frames whose slab rows one CTA holds
 constexpr int MAXGROUPS2 = 8;
 
 struct alignas(64) Tc2Params {
   CUtensorMap mx;                          // x as (channel, frame, utterance)
   CUtensorMap mw;                          // w as (tap*cin + channel, output channel)
   int32_t cin, k, dil, pad_left;
-  int32_t ntb;                             // 256-frame blocks per utterance
+  int32_t pair_n;                          // frames per pair tile: 256 (LINEAR), 128 (GATE: two accumulators)
+  int32_t nacc;                            // accumulators per CTA: 1, or 2 = (lo, hi) halves of a gate pair
+  int32_t ntb;                             // frame blocks per utterance
   int32_t ngroups, ntiles;                 // groups of two chunks; pair tiles
-  int32_t row0[MAXGROUPS2][2];             // filter row on lane 0 of the chunk of CTA r
+  int32_t row0[MAXGROUPS2][2];             // filter row on lane 0 of the chunk of CTA r (lo half for GATE)
   int32_t valid[MAXGROUPS2][2];
   int32_t slab_box_rows;                   // one TMA box per slab (128 + halo <= 256 rows)
   int32_t slab_stages, w_stages;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t 
   }
 }
 
-template <int OPF>
+template <int OPF, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
   constexpr int ESIZE = OPF == QVC_OPF_BF16 ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;
@@ -106,7 +106,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slab0 = smem_base;
   const uint32_t w0 = slab0 + p.slab_stages * p.slab_stage_bytes;
-  const uint32_t bar0 = w0 + p.w_stages * CHUNK_BYTES;
+  const uint32_t w_stage_bytes = (uint32_t)p.nacc * CHUNK_BYTES;
+  const uint32_t bar0 = w0 + p.w_stages * w_stage_bytes;
+  const int PN = p.pair_n, HN = p.pair_n >> 1;
   // barrier layout (same offsets in both CTAs): full_slab[SS] empty_slab[SS] full_w[WS] empty_w[WS]
   // tmem_full[2] tmem_empty[2], then the TMEM base word.  full_* and tmem_empty are only used in the leader.
   const uint32_t full_slab = bar0, empty_slab = full_slab + 8 * p.slab_stages;
@@ -152,7 +154,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         const int gi = tile % p.ngroups;
         const int rest = tile / p.ngroups;
         const int tb = rest % p.ntb, b = rest / p.ntb;
-        const int t0 = tb * PAIR_N + (int)rank * HALF_N;
+        const int t0 = tb * PN + (int)rank * HN;
         const int wrow = p.row0[gi][rank];
         for (int cc = 0; cc < n_cchunks; ++cc) {
           mbar_wait(empty_slab + 8 * s, ph ^ 1u);
@@ -161,8 +163,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
           for (int j = 0; j < p.k; ++j) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
-            if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * CHUNK_BYTES);
-            tma2_load_2d(w0 + ws * CHUNK_BYTES, &p.mw, lead_full_w + 8 * ws, j * p.cin + cc * KC, wrow);
+            if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * w_stage_bytes);
+            tma2_load_2d(w0 + ws * w_stage_bytes, &p.mw, lead_full_w + 8 * ws, j * p.cin + cc * KC, wrow);
+            if (EPI != QVC_EPI_LINEAR)       // hi half of the gate pair: the same lanes, H rows further down
+              tma2_load_2d(w0 + ws * w_stage_bytes + CHUNK_BYTES, &p.mw, lead_full_w + 8 * ws, j * p.cin + cc * KC,
+                           p.ep.half + wrow);
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -171,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(PAIR_N >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(PN >> 3) << 17) |
                              ((uint32_t)((2 * CHUNK_M) >> 4) << 24);
       const uint64_t desc_hi = smem_desc(0);
       uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
@@ -188,11 +193,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
             tc_fence_after();
             const uint32_t first = (cc | j) == 0 ? 0u : 1u;
             const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
-            const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * CHUNK_BYTES) & 0x3FFFFu) >> 4);
+            const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * w_stage_bytes) & 0x3FFFFu) >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma2<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              if (EPI != QVC_EPI_LINEAR) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma2<OPF>(d + (uint32_t)PN, adesc + (CHUNK_BYTES >> 4) + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              }
               tc2_commit(empty_w + 8 * ws);
               if (j == p.k - 1) tc2_commit(empty_slab + 8 * s);
             }
@@ -209,7 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
     // ===================== epilogue (warps 2..9, both CTAs): own 128 channels x 256 frames =====================
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
-    const int col_begin = h * HALF_N, col_end = col_begin + HALF_N;
+    const int col_begin = h * HN, col_end = col_begin + HN;
     const int lic = q * 32 + lane;
     const uint32_t lead_tmem_empty = map_to_cta(tmem_empty, 0);
     uint32_t ait = 0;
@@ -217,42 +227,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       const int gi = tile % p.ngroups;
       const int rest = tile / p.ngroups;
       const int tb = rest % p.ntb, b = rest / p.ntb;
-      const int t0 = tb * PAIR_N;
+      const int t0 = tb * PN;
       const uint32_t buf = ait & 1u;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
       const int nvalid = p.valid[gi][rank];
       const bool warp_live = q * 32 < nvalid;
-      LinCtx k;
-      {
-        const int n_w = p.row0[gi][rank] + q * 32;
-        const int n = n_w + lane;
-        k.sg = &p.ep.seg[(p.ep.nseg > 1 && n_w >= p.ep.seg[1].col0) ? 1 : 0];
-        const int c = n - k.sg->col0;
-        k.ok = warp_live && lic < nvalid && c >= 0 && c < k.sg->ncols;
-        k.all_ok = __all_sync(0xffffffffu, k.ok);
-        k.c = k.ok ? c : 0;
-        k.b = b;
-        k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
-      }
-      auto frames_at = [&](int col) -> int {
-        const int left = min(col_end - col, p.ep.out_rows - (t0 + col));
-        return left < 64 ? left : 64;
-      };
-      float r[64];
-      bool primed = false;
-      if (warp_live) {
-        const int nv = frames_at(col_begin);
-        if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
-        primed = true;
-      }
-      mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
-      tc_fence_after();
-      if (warp_live) {
-        for (int col = col_begin; col < col_end; col += 64) {
-          const int nv = frames_at(col);
-          if (nv <= 0) break;
-          if (!(primed && col == col_begin)) lin_load(k, t0 + col, nv, r);
-          lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)col);
+      if constexpr (EPI == QVC_EPI_LINEAR) {
+        LinCtx k;
+        {
+          const int n_w = p.row0[gi][rank] + q * 32;
+          const int n = n_w + lane;
+          k.sg = &p.ep.seg[(p.ep.nseg > 1 && n_w >= p.ep.seg[1].col0) ? 1 : 0];
+          const int c = n - k.sg->col0;
+          k.ok = warp_live && lic < nvalid && c >= 0 && c < k.sg->ncols;
+          k.all_ok = __all_sync(0xffffffffu, k.ok);
+          k.c = k.ok ? c : 0;
+          k.b = b;
+          k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
+        }
+        auto frames_at = [&](int col) -> int {
+          const int left = min(col_end - col, p.ep.out_rows - (t0 + col));
+          return left < 64 ? left : 64;
+        };
+        float r[64];
+        bool primed = false;
+        if (warp_live) {
+          const int nv = frames_at(col_begin);
+          if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
+          primed = true;
+        }
+        mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+        tc_fence_after();
+        if (warp_live) {
+          for (int col = col_begin; col < col_end; col += 64) {
+            const int nv = frames_at(col);
+            if (nv <= 0) break;
+            if (!(primed && col == col_begin)) lin_load(k, t0 + col, nv, r);
+            lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)col);
+          }
+        }
+      } else {
+        mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+        tc_fence_after();
+        if (warp_live) {
+          const int n = p.row0[gi][rank] + lic;
+          const bool ok = lic < nvalid;
+          const bool all_ok = __all_sync(0xffffffffu, ok);
+          const float* bias = p.ep.bias + (int64_t)b * p.ep.bias_bs;
+          const float bias_lo = ok ? bias[n] : 0.f, bias_hi = ok ? bias[p.ep.half + n] : 0.f;
+          for (int col = col_begin; col < col_end; col += 32) {
+            const int t = t0 + col;
+            const int nv = min(32, p.ep.out_rows - t);
+            if (nv <= 0) break;
+            epi_gate_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, all_ok, bias_lo, bias_hi, tbase + (uint32_t)col,
+                               tbase + (uint32_t)(PN + col));
+          }
         }
       }
       tc_fence_before();
@@ -270,11 +299,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
   }
 }
 
-template <int OPF>
+template <int OPF, int EPI>
 int launch2(const Tc2Params& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<OPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<OPF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -290,7 +319,7 @@ int launch2(const Tc2Params& p, int grid, size_t smem, cudaStream_t stream) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = tc_prof_next(&e0, &e1);
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e0, stream));
-  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<OPF>, p));
+  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<OPF, EPI>, p));
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e1, stream));
   return post_launch("conv_tc2_kernel");
 }
@@ -300,13 +329,18 @@ int launch2(const Tc2Params& p, int grid, size_t smem, cudaStream_t stream) {
 // Returns QVC_ERR_UNSUPPORTED (without touching the error string) when the layer is not a CTA-pair case.
 int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   if (!tc_env_int("QVC_TC_2CTA", 1)) return QVC_ERR_UNSUPPORTED;
-  if (a.epilogue != QVC_EPI_LINEAR) return QVC_ERR_UNSUPPORTED;
-  const int chunks = (a.cout + CHUNK_M - 1) / CHUNK_M;
-  if (chunks < 2 || (chunks & 1) || chunks / 2 > MAXGROUPS2) return QVC_ERR_UNSUPPORTED;
-  if (a.out_rows <= HALF_N) return QVC_ERR_UNSUPPORTED;                       // short series: conv_tc packs chunks instead
+  if (a.epilogue != QVC_EPI_LINEAR && a.epilogue != QVC_EPI_GATE) return QVC_ERR_UNSUPPORTED;
+  const bool gate = a.epilogue == QVC_EPI_GATE;
+  // GATE: CTA r owns channels [128 r, 128 r + 128) of the H = cout / 2 gate channels and holds two accumulators
+  // (tanh half, sigmoid half) of 128 frames; LINEAR: CTA r owns chunk 2 g + r and one accumulator of 256 frames.
+  const int span = gate ? a.cout / 2 : a.cout;
+  const int chunks = (span + CHUNK_M - 1) / CHUNK_M;
+  if (gate ? chunks != 2 : (chunks < 2 || (chunks & 1) || chunks / 2 > MAXGROUPS2)) return QVC_ERR_UNSUPPORTED;
+  const int pair_n = gate ? 128 : 256, half_n = pair_n / 2;
+  if (a.out_rows <= half_n) return QVC_ERR_UNSUPPORTED;                       // short series: conv_tc packs chunks instead
   const int halo = (a.k - 1) * a.dil;
-  if (HALF_N + halo > 256) return QVC_ERR_UNSUPPORTED;
-  if (a.nseg == 2 && (a.seg[1].col0 % 32 || a.seg[0].col0 % 32 || a.seg[0].ncols % 32)) return QVC_ERR_UNSUPPORTED;
+  if (half_n + halo > 256) return QVC_ERR_UNSUPPORTED;
+  if (!gate && a.nseg == 2 && (a.seg[1].col0 % 32 || a.seg[0].col0 % 32 || a.seg[0].ncols % 32)) return QVC_ERR_UNSUPPORTED;
   EncodeTiledFn encode = tc_get_encode();
   if (!encode) return QVC_ERR_UNSUPPORTED;
   const int esize = (int)opformat_bytes(a.opformat);
@@ -319,22 +353,24 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   Tc2Params p{};
   QVC_PROPAGATE(build_epi_params(a, &p.ep));
   p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
+  p.pair_n = pair_n;
+  p.nacc = gate ? 2 : 1;
   p.ngroups = chunks / 2;
   for (int gi = 0; gi < p.ngroups; ++gi)
     for (int r = 0; r < 2; ++r) {
       const int r0 = (2 * gi + r) * CHUNK_M;
       p.row0[gi][r] = r0;
-      p.valid[gi][r] = a.cout - r0 < CHUNK_M ? a.cout - r0 : CHUNK_M;
+      p.valid[gi][r] = span - r0 < CHUNK_M ? span - r0 : CHUNK_M;
     }
-  p.ntb = (a.out_rows + PAIR_N - 1) / PAIR_N;
+  p.ntb = (a.out_rows + pair_n - 1) / pair_n;
   p.ntiles = a.batch * p.ntb * p.ngroups;
-  p.slab_box_rows = (HALF_N + halo + 7) & ~7;
+  p.slab_box_rows = (half_n + halo + 7) & ~7;
   p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
   static const int stage_options[][2] = {{3, 8}, {3, 6}, {2, 6}, {2, 4}, {2, 3}, {2, 2}};
   size_t smem = 0;
   bool fits = false;
   for (const auto& opt : stage_options) {
-    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * CHUNK_BYTES + 1024 + 256;
+    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.nacc * CHUNK_BYTES + 1024 + 256;
     if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
   }
   if (!fits) return QVC_ERR_UNSUPPORTED;
@@ -363,8 +399,12 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   if (p.ntiles < pairs) pairs = p.ntiles;
   const int grid_env = tc_env_int("QVC_TC_GRID", 0);
   if (grid_env >= 2 && grid_env / 2 < pairs) pairs = grid_env / 2;
-  if (a.opformat == QVC_OPF_BF16) return launch2<QVC_OPF_BF16>(p, 2 * pairs, smem, stream);
-  return launch2<QVC_OPF_TF32>(p, 2 * pairs, smem, stream);
+  if (gate) {
+    if (a.opformat == QVC_OPF_BF16) return launch2<QVC_OPF_BF16, QVC_EPI_GATE>(p, 2 * pairs, smem, stream);
+    return launch2<QVC_OPF_TF32, QVC_EPI_GATE>(p, 2 * pairs, smem, stream);
+  }
+  if (a.opformat == QVC_OPF_BF16) return launch2<QVC_OPF_BF16, QVC_EPI_LINEAR>(p, 2 * pairs, smem, stream);
+  return launch2<QVC_OPF_TF32, QVC_EPI_LINEAR>(p, 2 * pairs, smem, stream);
 }
 
 }  // namespace qvc

@@ -36,6 +36,9 @@ GEOMS = [
     (3, 50, 512, 1280, 4, 1),     # ups.0 polyphase
     (1, 1, 192, 192, 5, 1),       # a single row
     (2, 5, 128, 128, 11, 5),      # series shorter than the filter span
+    (2, 700, 256, 512, 5, 1),     # ups.1 polyphase: CTA-pair kernel, two channel groups, ragged last frame block
+    (1, 257, 512, 1280, 4, 1),    # ups.0 polyphase: five channel groups, one frame past a pair tile
+    (2, 129, 256, 256, 7, 5),     # one frame into the second CTA's half
 ]
 
 
@@ -89,9 +92,10 @@ def test_conv_two_segments_wn_res_skip(be):
 
 @pytest.mark.parametrize("be", BACKENDS, ids=IDS)
 @pytest.mark.parametrize("per_utt_bias", [False, True])
-def test_conv_gate(be, per_utt_bias):
+@pytest.mark.parametrize("rows", [45, 300], ids=["R45", "R300"])      # R300: the CTA-pair (cta_group::2) gate kernel
+def test_conv_gate(be, per_utt_bias, rows):
     _, backend, opf = be
-    B, rows, H, k = 3, 45, 192, 5
+    B, H, k = 3, 192, 5
     g = torch.Generator(device="cpu").manual_seed(7)
     x = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
     w = to_op(torch.randn(2 * H, k, H, generator=g) / (H * k) ** 0.5, opf).to(DEV)
