@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QVC_ABI_VERSION 1
+#define QVC_ABI_VERSION 2
 
 typedef struct CUstream_st* qvc_stream_t;   /* == cudaStream_t */
 
@@ -154,6 +154,8 @@ typedef struct {
   const float* window;    /* (16) dec.stft.window                                              */
   const float* synth;     /* [4 bands][4 phases][17 taps] folded from dec.updown_filter and
                              dec.multistream_conv_post (see fold.py)                           */
+  const float* window_host; /* optional HOST copies of the two arrays above: when both are given */
+  const float* synth_host;  /* the coefficients travel as kernel parameters (constant bank)      */
 } qvc_tail_weights;
 
 /* post :: [B][frames][ld] fp32 with 72 live channels (band*18 + {0..8 log-mag, 9..17 phase});

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libqvc_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-QVC_ABI_VERSION = 1
+QVC_ABI_VERSION = 2
 QVC_NUM_LAYERS = 114
 
 OPF_F32, OPF_TF32, OPF_BF16 = 0, 1, 2
@@ -52,7 +52,7 @@ class SpkWeights(C.Structure):
 
 
 class TailWeights(C.Structure):
-    _fields_ = [("window", C.c_void_p), ("synth", C.c_void_p)]
+    _fields_ = [("window", C.c_void_p), ("synth", C.c_void_p), ("window_host", C.c_void_p), ("synth_host", C.c_void_p)]
 
 
 class Layer(C.Structure):

@@ -10,6 +10,9 @@
 // only re-read is the 7/64 halo.
 //
 // Algorithmic bytes per post-net frame: 72*4 read + 16*4 written = 352 B.
+#include <cstring>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace qvc {
@@ -30,6 +33,10 @@ struct TailParams {
   const float* synth;   // [4][4][17]
   float* wave;
   float* y_mb;
+  // host copies, present when the caller supplied them: as kernel parameters they live in the constant bank,
+  // so every coefficient is an FFMA operand instead of a shared-memory load
+  float Ec[4 * 4 * 17];
+  float Wc[16];
 };
 
 __constant__ float c_cos16[16] = {
@@ -38,7 +45,8 @@ __constant__ float c_cos16[16] = {
     -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f,
     0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
 
-__global__ void __launch_bounds__(NTHREADS) tail_kernel(const TailParams p) {
+template <bool CONST_COEF>
+__global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ TailParams p) {
   __shared__ __align__(16) float S[NFR][NCH];       // staged post-net frames
   __shared__ float Xf[4][NFR][17];                  // windowed frame samples (17: bank spread)
   __shared__ float Y[4][YW];                        // trimmed, normalised sub-band signal
@@ -54,20 +62,33 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const TailParams p) {
   const int ny = 4 * (F - 1);                       // sub-band samples per band
 
   if (tid < 16) {
-    const float w = p.window[tid];
+    const float w = CONST_COEF ? p.Wc[tid] : p.window[tid];
     W[tid] = w;
     W2[tid] = w * w;
   }
-  for (int i = tid; i < 4 * 4 * 17; i += NTHREADS) E[i] = p.synth[i];
+  if (!CONST_COEF)
+    for (int i = tid; i < 4 * 4 * 17; i += NTHREADS) E[i] = p.synth[i];
 
-  // 1. stage frames (coalesced 16-byte loads; a frame is 72 contiguous floats)
+  // 1. stage frames (coalesced 16-byte loads; a frame is 72 contiguous floats).  All loads of a thread are
+  // issued before the first store: the kernel was latency-bound here (43 % of its stall samples).
   const float* pb = p.post + (int64_t)b * F * p.ld;
-  for (int i = tid; i < NFR * (NCH / 4); i += NTHREADS) {
-    const int slot = i / (NCH / 4), c4 = i % (NCH / 4);
-    const int f = f_lo + slot;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f >= 0 && f < F) v = *reinterpret_cast<const float4*>(pb + (int64_t)f * p.ld + 4 * c4);
-    *reinterpret_cast<float4*>(&S[slot][4 * c4]) = v;
+  {
+    constexpr int ITEMS = NFR * (NCH / 4);
+    constexpr int PER_THREAD = (ITEMS + NTHREADS - 1) / NTHREADS;
+    float4 v[PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u) {
+      const int i = tid + u * NTHREADS;
+      const int slot = i / (NCH / 4), c4 = i % (NCH / 4);
+      const int f = f_lo + slot;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < ITEMS && f >= 0 && f < F) v[u] = __ldg(reinterpret_cast<const float4*>(pb + (int64_t)f * p.ld + 4 * c4));
+    }
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u) {
+      const int i = tid + u * NTHREADS;
+      if (i < ITEMS) *reinterpret_cast<float4*>(&S[i / (NCH / 4)][4 * (i % (NCH / 4))]) = v[u];
+    }
   }
   __syncthreads();
 
@@ -145,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const TailParams p) {
         for (int e = 0; e < 17; ++e) {
           const float yv = Y[s][tid + 16 - e];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) o[r] = fmaf(E[(s * 4 + r) * 17 + e], yv, o[r]);
+          for (int r = 0; r < 4; ++r) o[r] = fmaf(CONST_COEF ? p.Ec[(s * 4 + r) * 17 + e] : E[(s * 4 + r) * 17 + e], yv, o[r]);
         }
       }
       *reinterpret_cast<float4*>(p.wave + (int64_t)b * 4 * ny + 4 * (int64_t)q) =
@@ -171,8 +192,17 @@ extern "C" int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, in
   const int ny = 4 * (frames - 1);
   if (batch == 0 || ny == 0) return QVC_OK;
   QVC_REQUIRE(batch <= 65535, "qvc_tail: batch too large for one launch");
-  TailParams p{post, ld, frames, w->window, w->synth, wave, y_mb};
+  static TailParams p;                    // ~1.2 KB: not on the stack twice; filled and launched under the lock
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  p.post = post; p.ld = ld; p.frames = frames; p.window = w->window; p.synth = w->synth; p.wave = wave; p.y_mb = y_mb;
   dim3 grid((ny + TQ - 1) / TQ, batch);
-  tail_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(p);
+  if (w->synth_host && w->window_host) {
+    memcpy(p.Ec, w->synth_host, sizeof(p.Ec));
+    memcpy(p.Wc, w->window_host, sizeof(p.Wc));
+    tail_kernel<true><<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(p);
+  } else {
+    tail_kernel<false><<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(p);
+  }
   return post_launch("tail_kernel");
 }

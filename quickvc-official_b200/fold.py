@@ -224,6 +224,9 @@ def fold_state_dict(sd: Mapping[str, Tensor], opformat: int) -> Folded:
     f.tensors["tail.window"] = sd["dec.stft.window"].detach().float().contiguous()
     f.tensors["tail.synth"] = synthesis_polyphase(sd["dec.updown_filter"].detach(),
                                                   _weight(sd, "dec.multistream_conv_post")).float().contiguous()
+    # host copies: the tail kernel takes its 16 + 272 coefficients as kernel parameters (constant bank)
+    f.tensors["tail.window_host"] = f.tensors["tail.window"].cpu().contiguous()
+    f.tensors["tail.synth_host"] = f.tensors["tail.synth"].cpu().contiguous()
     return f
 
 
@@ -244,4 +247,5 @@ def build_model_struct(f: Folded, opformat: int, backend: int, chunk_utts: int) 
         m.spk.bias[l] = t[f"spk.bias.{l}"].data_ptr()
     m.spk.lin_w, m.spk.lin_b = t["spk.lin_w"].data_ptr(), t["spk.lin_b"].data_ptr()
     m.tail.window, m.tail.synth = t["tail.window"].data_ptr(), t["tail.synth"].data_ptr()
+    m.tail.window_host, m.tail.synth_host = t["tail.window_host"].data_ptr(), t["tail.synth_host"].data_ptr()
     return m

@@ -72,7 +72,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(capi.EpiSegment) == 24 + 4 * 24
     assert ctypes.sizeof(capi.Layer) == 40
     assert ctypes.sizeof(capi.ConvArgs) == 24 + 16 + 24 + 16 + 8 + 2 * 120 + 3 * 24 + 8
-    assert ctypes.sizeof(capi.Model) == 16 + 114 * 40 + 24 + 11 * 8 + 2 * 8
+    assert ctypes.sizeof(capi.Model) == 16 + 114 * 40 + 24 + 11 * 8 + 4 * 8
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted")

@@ -177,6 +177,13 @@ def test_tail_matches_oracle(frames, batch, sd):
     want = F.conv1d(up, p.weight("dec.multistream_conv_post"), padding=31)
     assert synth.max_abs(ymb, y) < 2e-5 * float(y.abs().max())
     assert synth.max_abs(wave, want) < 2e-5 * float(want.abs().max())
+    # same kernel with the coefficients passed as kernel parameters (host copies given): identical arithmetic
+    tw2 = capi.TailWeights(win.data_ptr(), syn.data_ptr(), f.tensors["tail.window_host"].data_ptr(),
+                           f.tensors["tail.synth_host"].data_ptr())
+    wave2 = torch.full_like(wave, float("nan"))
+    capi.check(lib.qvc_tail(C.byref(tw2), post_sm.data_ptr(), 72, batch, frames, wave2.data_ptr(), None, stream()), "qvc_tail")
+    torch.cuda.synchronize()
+    assert torch.equal(wave2, wave)
 
 
 @pytest.mark.parametrize("bm,tm", [(1, 129), (1, 250), (1, 500), (1, 1500), (3, 100), (1, 128), (9, 7)])
