@@ -336,18 +336,28 @@ def run_ours(args, rank, local_rank, world):
                                  "roofline_frac_of_bf16_sustained": flops / (ms_b * 1e-3) / 1e12 / pk["bf16_sustained"],
                                  "tolerance": "waveform max-abs 2e-3, per-stage rel-L2 1.5e-2 (tests/test_gpu_infer.py)"}
             del nb
-        u5, m5, n5 = unit[:1, :, :250].contiguous(), mel[:, :, :250].contiguous(), noise[:1, :, :250].contiguous()
-        lat = []
-        for i in range(60):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            net.infer(u5, m5, noise=n5)
-            e.record()
-            torch.cuda.synchronize()
-            if i >= 10:
-                lat.append(s.elapsed_time(e))
-        lat.sort()
-        line["latency_5s_clip_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))]}
+        # single-call latency: the 5 s clip of the metric, and BASELINE.json configs[3] (0.5 s chunks), each through
+        # infer(unit, mel) as convert.py calls it and with the target-speaker embedding cached (the reference
+        # recomputes it on every call, models.py:635)
+        def latency(fn, n=110):
+            lat = []
+            for i in range(n):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                torch.cuda.synchronize()
+                if i >= 10:
+                    lat.append(s.elapsed_time(e))
+            lat.sort()
+            return {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))]}
+
+        m5 = mel[:, :, :250].contiguous()
+        emb = net.embed_speaker(m5)
+        for name, frames in (("latency_5s_clip_ms", 250), ("latency_0p5s_chunk_ms", 25)):
+            u1, n1 = unit[:1, :, :frames].contiguous(), noise[:1, :, :frames].contiguous()
+            line[name] = latency(lambda: net.infer(u1, m5, noise=n1))
+            line[name]["cached_speaker"] = latency(lambda: net.infer_with_embedding(u1, emb, noise=n1))
 
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1

@@ -434,6 +434,12 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   }
   int ntime = (ACC_COLS / g) & ~31;
   if (rows32 < ntime) ntime = rows32;
+  // Small problems (single clips, streaming chunks): a tile's K loop is a serial chain of MMAs whose cost
+  // barely shrinks with N (N = 64: ~94 cycles, N = 256: ~190), so narrower tiles on more SMs cut latency.
+  {
+    const int groups = paired ? p.ngroups : (( (a.cout + CHUNK_M - 1) / CHUNK_M) + g - 1) / g;
+    while (ntime > 64 && (long)a.batch * ((a.out_rows + ntime - 1) / ntime) * groups < sm_count()) ntime = (ntime / 2 + 31) & ~31;
+  }
   const int n_env = env_int("QVC_TC_N", 0);
   if (n_env >= 32 && n_env % 32 == 0 && n_env <= ntime) ntime = n_env;
   p.ntime = ntime;

@@ -364,6 +364,8 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
     }
   p.ntb = (a.out_rows + pair_n - 1) / pair_n;
   p.ntiles = a.batch * p.ntb * p.ngroups;
+  // too few pair tiles to occupy the machine: conv_tc with narrower tiles has the shorter critical path
+  if (p.ntiles < tc_sm_count() / 4 && !tc_env_int("QVC_TC_2CTA_FORCE", 0)) return QVC_ERR_UNSUPPORTED;
   p.slab_box_rows = (half_n + halo + 7) & ~7;
   p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
   static const int stage_options[][2] = {{3, 8}, {3, 6}, {2, 6}, {2, 4}, {2, 3}, {2, 2}};

@@ -80,6 +80,15 @@ lstm_recurrent_kernel(const RecParams p) {
   }
   cluster.sync();
 
+  // this thread's slice of W_hh (unit u, 4 gates, 32 of the 256 k) stays in registers for all steps: the
+  // per-step loop then reads only h from shared memory (the W reads were 4 of every 11 LDS.128)
+  float4 wreg[4][HID / 32];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int kk = 0; kk < HID / 32; ++kk)
+      wreg[g][kk] = *reinterpret_cast<const float4*>(Wsm + (u * 4 + g) * HID + kk * 32 + ks * 4);
+
   float* remote[CLUSTER];
 #pragma unroll
   for (int r = 0; r < CLUSTER; ++r) remote[r] = cluster.map_shared_rank(hbuf, r);
@@ -92,22 +101,19 @@ lstm_recurrent_kernel(const RecParams p) {
 #pragma unroll
       for (int s = 0; s < MAXSEQ; ++s) acc[g][s] = 0.f;
 
-#pragma unroll 2
+#pragma unroll
     for (int kk = 0; kk < HID / 32; ++kk) {
       const int k = kk * 32 + ks * 4;
-      float4 wv[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) wv[g] = *reinterpret_cast<const float4*>(Wsm + (u * 4 + g) * HID + k);
 #pragma unroll
       for (int s = 0; s < MAXSEQ; ++s) {
         if (s < ns) {
           const float4 hv = *reinterpret_cast<const float4*>(hc + s * HID + k);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            acc[g][s] = fmaf(wv[g].x, hv.x, acc[g][s]);
-            acc[g][s] = fmaf(wv[g].y, hv.y, acc[g][s]);
-            acc[g][s] = fmaf(wv[g].z, hv.z, acc[g][s]);
-            acc[g][s] = fmaf(wv[g].w, hv.w, acc[g][s]);
+            acc[g][s] = fmaf(wreg[g][kk].x, hv.x, acc[g][s]);
+            acc[g][s] = fmaf(wreg[g][kk].y, hv.y, acc[g][s]);
+            acc[g][s] = fmaf(wreg[g][kk].z, hv.z, acc[g][s]);
+            acc[g][s] = fmaf(wreg[g][kk].w, hv.w, acc[g][s]);
           }
         }
       }

@@ -1,0 +1,38 @@
+"""p50 / p99 latency of single-utterance calls (BASELINE.json configs[0] shape 5 s, configs[3] 0.5 s chunks)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from quickvc_official_b200 import SynthesizerTrn  # noqa: E402
+
+cfg = bench.model_cfg()
+sd = bench.random_init_state_dict(cfg)
+dev = torch.device("cuda:0")
+for precision in ("tf32", "bf16"):
+    net = SynthesizerTrn(641, 32, **cfg, precision=precision).eval()
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    for T in (250, 25):
+        g = torch.Generator().manual_seed(1)
+        unit = torch.randn(1, 256, T, generator=g).to(dev)
+        mel = (torch.randn(1, 80, 250, generator=g) * 2 - 5).to(dev)
+        noise = torch.randn(1, 192, T, generator=g).to(dev)
+        emb = net.embed_speaker(mel)
+        for name, fn in (("infer(unit, mel)", lambda: net.infer(unit, mel, noise=noise)),
+                         ("cached speaker", lambda: net.infer_with_embedding(unit, emb, noise=noise))):
+            lat = []
+            for i in range(210):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                torch.cuda.synchronize()
+                if i >= 10:
+                    lat.append(s.elapsed_time(e))
+            lat.sort()
+            print(f"{precision} T={T:3d} {name:18s} p50 {lat[len(lat) // 2]:.3f} ms  p99 {lat[int(len(lat) * 0.99)]:.3f} ms", flush=True)
