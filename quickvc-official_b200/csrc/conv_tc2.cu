@@ -31,6 +31,7 @@ struct alignas(64) Tc2Params {
   int32_t cin, k, dil, pad_left;
   int32_t pair_n;                          // frames per pair tile: 256 (LINEAR), 128 (GATE: two accumulators)
   int32_t nacc;                            // accumulators per CTA: 1, or 2 = (lo, hi) halves of a gate pair
+  int32_t nbuf;                            // accumulator sets in TMEM: 2 (epilogue overlaps the next tile), or 1 when nacc * pair_n = 512
   int32_t ntb;                             // frame blocks per utterance
   int32_t ngroups, ntiles;                 // groups of two chunks; pair tiles
   int32_t row0[MAXGROUPS2][2];             // filter row on lane 0 of the chunk of CTA r (lo half for GATE)
@@ -181,8 +182,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       const uint64_t desc_hi = smem_desc(0);
       uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs, ++ait) {
-        const uint32_t buf = ait & 1u;
-        mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this set
+        const uint32_t buf = p.nbuf == 2 ? (ait & 1u) : 0u;
+        const uint32_t bph = p.nbuf == 2 ? ((ait >> 1) & 1u) : (ait & 1u);
+        mbar_wait(tmem_empty + 8 * buf, bph ^ 1u);                 // both CTAs' epilogues drained this set
         tc_fence_after();
         const uint32_t d = tmem_base + buf * ACC_COLS;
         for (int cc = 0; cc < n_cchunks; ++cc) {
@@ -228,7 +230,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       const int rest = tile / p.ngroups;
       const int tb = rest % p.ntb, b = rest / p.ntb;
       const int t0 = tb * PN;
-      const uint32_t buf = ait & 1u;
+      const uint32_t buf = p.nbuf == 2 ? (ait & 1u) : 0u;
+      const uint32_t bph = p.nbuf == 2 ? ((ait >> 1) & 1u) : (ait & 1u);
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
       const int nvalid = p.valid[gi][rank];
       const bool warp_live = q * 32 < nvalid;
@@ -256,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
           primed = true;
         }
-        mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+        mbar_wait(tmem_full + 8 * buf, bph);
         tc_fence_after();
         if (warp_live) {
           for (int col = col_begin; col < col_end; col += 64) {
@@ -267,7 +270,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           }
         }
       } else {
-        mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
+        mbar_wait(tmem_full + 8 * buf, bph);
         tc_fence_after();
         if (warp_live) {
           const int n = p.row0[gi][rank] + lic;
@@ -336,7 +339,7 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   const int span = gate ? a.cout / 2 : a.cout;
   const int chunks = (span + CHUNK_M - 1) / CHUNK_M;
   if (gate ? chunks != 2 : (chunks < 2 || (chunks & 1) || chunks / 2 > MAXGROUPS2)) return QVC_ERR_UNSUPPORTED;
-  const int pair_n = gate ? 128 : 256, half_n = pair_n / 2;
+  const int pair_n = gate ? (tc_env_int("QVC_TC_GATE_N", 128) == 256 ? 256 : 128) : 256, half_n = pair_n / 2;
   if (a.out_rows <= half_n) return QVC_ERR_UNSUPPORTED;                       // short series: conv_tc packs chunks instead
   const int halo = (a.k - 1) * a.dil;
   if (half_n + halo > 256) return QVC_ERR_UNSUPPORTED;
@@ -355,6 +358,7 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
   p.pair_n = pair_n;
   p.nacc = gate ? 2 : 1;
+  p.nbuf = p.nacc * pair_n > ACC_COLS ? 1 : 2;
   p.ngroups = chunks / 2;
   for (int gi = 0; gi < p.ngroups; ++gi)
     for (int r = 0; r < 2; ++r) {

@@ -47,7 +47,6 @@ __constant__ float c_cos16[16] = {
 
 template <bool CONST_COEF>
 __global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ TailParams p) {
-  __shared__ __align__(16) float S[NFR][NCH];       // staged post-net frames
   __shared__ float Xf[4][NFR][17];                  // windowed frame samples (17: bank spread)
   __shared__ float Y[4][YW];                        // trimmed, normalised sub-band signal
   __shared__ float E[4 * 4 * 17];                   // synthesis filter
@@ -69,41 +68,35 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ 
   if (!CONST_COEF)
     for (int i = tid; i < 4 * 4 * 17; i += NTHREADS) E[i] = p.synth[i];
 
-  // 1. stage frames (coalesced 16-byte loads; a frame is 72 contiguous floats).  All loads of a thread are
-  // issued before the first store: the kernel was latency-bound here (43 % of its stall samples).
   const float* pb = p.post + (int64_t)b * F * p.ld;
-  {
-    constexpr int ITEMS = NFR * (NCH / 4);
-    constexpr int PER_THREAD = (ITEMS + NTHREADS - 1) / NTHREADS;
-    float4 v[PER_THREAD];
-#pragma unroll
-    for (int u = 0; u < PER_THREAD; ++u) {
-      const int i = tid + u * NTHREADS;
-      const int slot = i / (NCH / 4), c4 = i % (NCH / 4);
-      const int f = f_lo + slot;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < ITEMS && f >= 0 && f < F) v[u] = __ldg(reinterpret_cast<const float4*>(pb + (int64_t)f * p.ld + 4 * c4));
-    }
-#pragma unroll
-    for (int u = 0; u < PER_THREAD; ++u) {
-      const int i = tid + u * NTHREADS;
-      if (i < ITEMS) *reinterpret_cast<float4*>(&S[i / (NCH / 4)][4 * (i % (NCH / 4))]) = v[u];
-    }
-  }
-  __syncthreads();
+  __syncthreads();                                  // W / W2 / E visible
 
   // 2. one (frame, band) per thread: polar -> inverse real DFT -> window
   {
     const int slot = tid >> 2, s = tid & 3;
     const int f = f_lo + slot;
     if (slot < NFR && f >= 0 && f < F) {
+      // the 18 inputs of this (frame, band) straight from global memory: 72 contiguous bytes, 8-byte aligned;
+      // the four bands of a frame and consecutive frames are contiguous, so a warp reads one 2304-byte run.
+      // (Staging whole frames through shared memory first cost 20 KB per CTA and a load phase nothing overlapped:
+      // the kernel sat at 4 CTAs per SM, 43 % of its stall samples in that phase.)
+      float in18[18];
+      {
+        const float2* src = reinterpret_cast<const float2*>(pb + (int64_t)f * p.ld + 18 * s);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float2 t2 = __ldg(src + k);
+          in18[2 * k] = t2.x;
+          in18[2 * k + 1] = t2.y;
+        }
+      }
       float re[9], im[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         // SFU paths (ex2 / sin / cos approx, abs error ~5e-7 after the 2*pi range reduction): the libm
         // versions made this kernel instruction-bound at 18 % of the HBM roofline
-        const float mag = __expf(S[slot][18 * s + k]);
-        const float xp = S[slot][18 * s + 9 + k];
+        const float mag = __expf(in18[k]);
+        const float xp = in18[9 + k];
         const float xr = fmaf(-6.28318530717958647692f, rintf(xp * 0.15915494309189533577f), xp);
         const float ph = 3.14159265358979323846f * __sinf(xr);            // in [-pi, pi]
         float sn, cs;
