@@ -295,8 +295,16 @@ def run_ours(args, rank, local_rank, world):
     achieved = conv_flops / (conv_ms_step * 1e-3) / 1e12
     tf32 = args.precision != "bf16"
     peak = pk["bf16_sustained"] * (0.5 if tf32 else 1.0)
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.precision == "tf32" and B == 64 and T == 500:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["conv_tc"]["dram_bytes_per_launch"]
+        traffic_note = ("DRAM bytes (read + write) per launch, averaged over the kernel's launches of one step: " + tj["source"])
     roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": traffic_note,
         "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM series convolution)",
         "launches_per_step": int(conv_launches), "avg_launch_us": conv_ms_step * 1e3 / max(1, conv_launches),
         "kernel_ms_per_step": conv_ms_step, "kernel_share_of_step": conv_ms_step / ms,
@@ -343,7 +351,9 @@ def run_ours(args, rank, local_rank, world):
                                                            wave.data_ptr(), None, stream), "qvc_tail"), 20, 3)
         tail_bytes = B * frames_post * TAIL_BYTES_PER_POST_FRAME
         line["tail_roofline"] = {"bound": "hbm", "achieved": tail_bytes / (ms_tail * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                 "frac": tail_bytes / (ms_tail * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "ms": ms_tail,
+                                 "frac": tail_bytes / (ms_tail * 1e-3) / 1e9 / pk["hbm"],
+                                 "traffic": (tj["tail"]["dram_bytes_per_launch"] if traffic is not None else None), "ms": ms_tail,
+                                 "algorithmic_bytes": tail_bytes,
                                  "peak_source": pk["source"]}
         # the separately reported bf16 mode, and the p50 latency of one 5 s clip
         if args.precision == "tf32":
