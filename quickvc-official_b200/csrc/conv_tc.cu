@@ -169,9 +169,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             for (int ci = 0; ci < gs; ++ci) {
               const uint64_t adesc = desc_hi | (uint64_t)(((wst + (uint32_t)ci * CHUNK_BYTES) & 0x3FFFFu) >> 4);
               const uint32_t d = dbase + (uint32_t)(ci * N);
+              if (p.debug & 16) {
+                // timing experiment only (garbage A): A operand from TMEM -- the other accumulator set
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)      // +32 bytes per K step = +2 in the (addr >> 4) field
-                umma<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts<OPF>(d, tmem_base + (buf ^ 1u) * ACC_COLS + 8 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)      // +32 bytes per K step = +2 in the (addr >> 4) field
+                  umma<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              }
             }
             tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
             if (j == p.k - 1) tc_commit(empty_slab + 8 * s);
