@@ -116,6 +116,16 @@ typedef struct {
 
 int qvc_conv1d(const qvc_conv_args* args, qvc_stream_t stream);
 
+/* One whole WN layer (modules.py:88-112) in one launch: `in_layer` (QVC_EPI_GATE) followed by `res_skip`
+ * (QVC_EPI_LINEAR, k = 1) whose input is the gate output.  Equivalent to qvc_conv1d(in_layer) then
+ * qvc_conv1d(res_skip) with res_skip->x == in_layer->seg[0].op, except that the gated activations stay in shared
+ * memory (in_layer->seg[0] and res_skip->x are ignored) and that res_skip's operand output must not alias
+ * in_layer->x (other tiles still read it as halo: ping-pong the operand copy of x between layers).
+ * Returns QVC_ERR_UNSUPPORTED, leaving the error string alone, when the shapes are not ones the fused kernel
+ * handles (it needs the tcgen05 back end, 128 < H <= 256 gate channels, enough tiles to fill the machine);
+ * the caller then issues the two calls. */
+int qvc_wn_layer(const qvc_conv_args* in_layer, const qvc_conv_args* res_skip, qvc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Layout / format helpers
  * ------------------------------------------------------------------------------------------- */

@@ -78,6 +78,7 @@ class Taps(C.Structure):
 # every symbol include/qvc_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qvc_conv1d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "qvc_wn_layer": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvArgs), C.c_void_p]),
     "qvc_to_series_major": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "qvc_from_series_major": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "qvc_spk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

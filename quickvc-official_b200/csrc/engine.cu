@@ -39,7 +39,7 @@ struct Shapes { int B, T, n_embed; int cb; };
 
 struct Buffers {
   // whole batch
-  void *unitO, *xO, *actsO, *skipO, *zO;
+  void *unitO, *xO, *xO2, *actsO, *skipO, *zO;
   float *noiseT, *xR, *skipR, *zR, *tapA, *tapB, *condvec, *g;
   void* spk_ws; size_t spk_ws_bytes;
   // per decoder sub-batch
@@ -68,6 +68,7 @@ size_t carve(const qvc_model* m, const Shapes& s, int mel_batch, int mel_frames,
   b->unitO = a.take(n1 * UNIT_CH * E);
   b->noiseT = (float*)a.take(n1 * HID * 4);
   b->xR = (float*)a.take(n1 * HID * 4);      b->xO = a.take(n1 * HID * E);
+  b->xO2 = a.take(n1 * HID * E);             // ping-pong partner of xO (fused WN layers)
   b->actsO = a.take(n1 * HID * E);
   b->skipR = (float*)a.take(n1 * HID * 4);   b->skipO = a.take(n1 * HID * E);
   b->zR = (float*)a.take(n1 * HID * 4);      b->zO = a.take(n1 * HID * E);
@@ -125,13 +126,16 @@ int run(const Ctx& c, const qvc_conv_args& a) { return qvc_conv1d(&a, (qvc_strea
 int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, int n_layers,
            const float* gate_bias, int64_t gate_bias_bs, int gate_bias_layer_stride) {
   const int64_t bs = (int64_t)T * HID;
+  // the operand copy of x ping-pongs between two buffers: a fused layer (qvc_wn_layer) writes the new x while other
+  // tiles of the same launch still read the old one as convolution halo
+  const void* x_in = bf.xO;
+  void* x_out = bf.xO2;
   for (int i = 0; i < n_layers; ++i) {
-    qvc_conv_args a = layer_args(c, l_in + i, tens(bf.xO, bs, HID), B, T, T);
+    qvc_conv_args a = layer_args(c, l_in + i, tens(x_in, bs, HID), B, T, T);
     a.epilogue = QVC_EPI_GATE;
     if (gate_bias) { a.bias = gate_bias + (int64_t)i * gate_bias_layer_stride; a.bias_bstride = gate_bias_bs; }
     a.seg[0] = seg(0, HID);
     a.seg[0].op = tens(bf.actsO, bs, HID);
-    QVC_PROPAGATE(run(c, a));
 
     qvc_conv_args r = layer_args(c, l_rs + i, tens(bf.actsO, bs, HID), B, T, T);
     if (i < n_layers - 1) {
@@ -139,7 +143,7 @@ int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, in
       r.seg[0] = seg(0, HID);                       // residual half: x += ...
       r.seg[0].res = tens(bf.xR, bs, HID);
       r.seg[0].raw = tens(bf.xR, bs, HID);
-      r.seg[0].op = tens(bf.xO, bs, HID);
+      r.seg[0].op = tens(x_out, bs, HID);
       r.seg[1] = seg(HID, HID);                     // skip half: out += ...
       if (i > 0) r.seg[1].accin = tens(bf.skipR, bs, HID);
       r.seg[1].raw = tens(bf.skipR, bs, HID);
@@ -149,7 +153,17 @@ int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, in
       if (i > 0) r.seg[0].accin = tens(bf.skipR, bs, HID);
       r.seg[0].op = tens(bf.skipO, bs, HID);
     }
-    QVC_PROPAGATE(run(c, r));
+    int st = QVC_ERR_UNSUPPORTED;
+    if (c.m->backend == QVC_BACKEND_TCGEN05) st = qvc_wn_layer(&a, &r, (qvc_stream_t)c.st);
+    if (st == QVC_ERR_UNSUPPORTED) {
+      QVC_PROPAGATE(run(c, a));
+      QVC_PROPAGATE(run(c, r));
+    } else {
+      QVC_PROPAGATE(st);
+    }
+    const void* tmp = x_in;
+    x_in = x_out;
+    x_out = const_cast<void*>(tmp);
   }
   return QVC_OK;
 }

@@ -29,11 +29,10 @@ def to_op(x: torch.Tensor, opf: int) -> torch.Tensor:
     return fold.to_operand(x, opf)
 
 
-def conv1d(x, w, bias, *, k, dil, pad_left, out_rows, opf, backend, epilogue=capi.EPI_LINEAR, segs=(),
-           noise=None, aux0=None, aux1=None, bias_bstride=0):
+def make_args(x, w, bias, *, k, dil, pad_left, out_rows, opf, backend, epilogue=capi.EPI_LINEAR, segs=(),
+              noise=None, aux0=None, aux1=None, bias_bstride=0) -> capi.ConvArgs:
     """x [B][rows][cin] operand tensor, w [cout][k][cin] operand tensor; segs: list of dicts with
-    col0, ncols, alpha, beta, slope, res, accin, raw, op tensors."""
-    lib = capi.load()
+    col0, ncols, alpha, beta, slope, res, accin, raw, op tensors.  The caller keeps the tensors alive."""
     a = capi.ConvArgs()
     a.x = tref(x)
     a.batch, a.x_rows, a.out_rows, a.cin = x.shape[0], x.shape[1], out_rows, x.shape[2]
@@ -49,7 +48,12 @@ def conv1d(x, w, bias, *, k, dil, pad_left, out_rows, opf, backend, epilogue=cap
         g.res, g.accin, g.raw, g.op = (tref(s.get(n)) for n in ("res", "accin", "raw", "op"))
     a.noise, a.aux0, a.aux1 = tref(noise), tref(aux0), tref(aux1)
     a.opformat, a.backend = opf, backend
-    capi.check(lib.qvc_conv1d(C.byref(a), stream()), "qvc_conv1d")
+    return a
+
+
+def conv1d(x, w, bias, **kw):
+    a = make_args(x, w, bias, **kw)
+    capi.check(capi.load().qvc_conv1d(C.byref(a), stream()), "qvc_conv1d")
 
 
 def ref_conv(x, w, k, dil, pad_left, out_rows):

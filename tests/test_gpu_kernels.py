@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import synth
-from gpu_util import conv1d, op_dtype, ref_conv, stream, to_op, tref
+from gpu_util import conv1d, make_args, op_dtype, ref_conv, stream, to_op, tref
 from oracle import qvc_oracle
 from quickvc_official_b200 import capi, fold
 
@@ -88,6 +88,50 @@ def test_conv_two_segments_wn_res_skip(be):
     acc = ref_conv(acts.cpu().float(), w.cpu().float(), 1, 1, 0, rows) + bias.cpu().double()
     assert float((x.cpu().double() - (x0.cpu().double() + acc[..., :H])).abs().max()) < _tol(opf) * 4
     assert float((skip.cpu().double() - (skip0.cpu().double() + acc[..., H:])).abs().max()) < _tol(opf) * 4
+
+
+@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("last", [False, True], ids=["res_skip", "skip_only"])
+def test_fused_wn_layer_equals_the_two_convolutions(opf, last):
+    """qvc_wn_layer (one CTA-pair kernel, activations kept in shared memory) against qvc_conv1d(in_layer) +
+    qvc_conv1d(res_skip) on the same operands: same arithmetic, so the results must agree to accumulation noise."""
+    lib = capi.load()
+    B, rows, H, k = 9, 700, 192, 5                  # 9 x 6 pair tiles; the last frame block is ragged (700 = 5*128 + 60)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
+    w_in = to_op(torch.randn(2 * H, k, H, generator=g) / (H * k) ** 0.5, opf).to(DEV)
+    gbias = torch.randn(B, 2 * H, generator=g).to(DEV)
+    rs_out = H if last else 2 * H
+    w_rs = to_op(torch.randn(rs_out, 1, H, generator=g) / H ** 0.5, opf).to(DEV)
+    b_rs = torch.randn(rs_out, generator=g).to(DEV)
+    xr0 = torch.randn(B, rows, H, generator=g).to(DEV)
+    sk0 = torch.randn(B, rows, H, generator=g).to(DEV)
+    be = capi.BACKEND_TCGEN05
+
+    def run(fused):
+        xr, sk = xr0.clone(), sk0.clone()
+        acts = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+        xo = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+        a = make_args(x, w_in, gbias, k=k, dil=1, pad_left=2, out_rows=rows, opf=opf, backend=be, epilogue=capi.EPI_GATE,
+                      segs=[dict(col0=0, ncols=H, op=acts)], bias_bstride=2 * H)
+        if last:
+            segs = [dict(col0=0, ncols=H, accin=sk, op=xo)]
+        else:
+            segs = [dict(col0=0, ncols=H, res=xr, raw=xr, op=xo), dict(col0=H, ncols=H, accin=sk, raw=sk)]
+        r = make_args(acts, w_rs, b_rs, k=1, dil=1, pad_left=0, out_rows=rows, opf=opf, backend=be, segs=segs)
+        if fused:
+            capi.check(lib.qvc_wn_layer(C.byref(a), C.byref(r), stream()), "qvc_wn_layer")
+        else:
+            capi.check(lib.qvc_conv1d(C.byref(a), stream()), "qvc_conv1d")
+            capi.check(lib.qvc_conv1d(C.byref(r), stream()), "qvc_conv1d")
+        torch.cuda.synchronize()
+        return xr.cpu(), sk.cpu(), xo.float().cpu()
+
+    want, got = run(False), run(True)
+    tol = 2e-5 if opf == capi.OPF_TF32 else 1e-2
+    for name, w, gt in zip(("x", "skip", "x operand"), want, got):
+        scale = float(w.abs().max()) + 1e-6
+        assert float((w - gt).abs().max()) < tol * scale, name
 
 
 @pytest.mark.parametrize("be", BACKENDS, ids=IDS)
