@@ -141,3 +141,28 @@ def test_argument_errors(sd, model_cfg):
         net.infer(torch.zeros(1, 256, 8), torch.zeros(1, 80, 130))
     empty = net.infer(torch.zeros(0, 256, 8, device=DEV), torch.zeros(1, 80, 130, device=DEV))
     assert empty.shape == (0, 1, 2560)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_pair_kernels_on_the_golden_case(precision, sd, model_cfg, monkeypatch):
+    """The CTA-pair (cta_group::2) convolutions and the fused WN-layer kernel are chosen only for shapes that fill
+    the machine; QVC_TC_2CTA_FORCE selects them for the small golden case too, so they are checked per stage
+    against the reference's own outputs (not only at full size)."""
+    monkeypatch.setenv("QVC_TC_2CTA_FORCE", "1")
+    wave_tol, stage_tol = MODES[(precision, "tcgen05")]
+    b, t, bm, tm = GOLDEN_CASES["small"]
+    unit, mel, noise = synth.synthetic_inputs(b, t, bm, tm, 0)
+    gold = load_golden("small")
+    net = get_net(sd, model_cfg, precision, "tcgen05")
+    taps = {}
+    before = capi.launch_count()
+    wave = net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV), taps=taps)
+    torch.cuda.synchronize()
+    forced = capi.launch_count() - before
+    for n, ref in gold.items():
+        assert synth.rel_l2(taps[n], ref) < stage_tol, n
+    assert synth.max_abs(wave, gold["wave"]) < wave_tol
+    monkeypatch.delenv("QVC_TC_2CTA_FORCE")
+    before = capi.launch_count()
+    net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
+    assert capi.launch_count() - before > forced          # the fused WN layers save one launch each
