@@ -423,8 +423,15 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
     // the same issue slot as an N = 128 one, so wide-N tiles win even though the slab is re-read once per
     // chunk.  Short series put more chunks on a tile instead of frames.
     g = 1;
-    if (rows32 <= 128 && chunks >= 2) g = 2;
-    if (rows32 <= 64 && chunks >= 4) g = 4;
+    {
+      // ... but only when there are tiles to spare: with few tiles (single clips, streaming chunks) one chunk per
+      // tile keeps the serial MMA chain of a CTA short and spreads the chunks over more SMs
+      const long tiles_g1 = (long)a.batch * ((a.out_rows + 255) / 256) * chunks;
+      if (tiles_g1 >= 2L * sm_count()) {
+        if (rows32 <= 128 && chunks >= 2) g = 2;
+        if (rows32 <= 64 && chunks >= 4) g = 4;
+      }
+    }
     const int g_env = env_int("QVC_TC_G", 0);
     if (g_env >= 1 && g_env <= MAXG && g_env <= chunks) g = g_env;
     p.ngroups = (chunks + g - 1) / g;
