@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QVC_ABI_VERSION 2
+#define QVC_ABI_VERSION 3
 
 typedef struct CUstream_st* qvc_stream_t;   /* == cudaStream_t */
 
@@ -71,7 +71,7 @@ typedef struct {
 } qvc_tensor;
 
 typedef enum {
-  QVC_EPI_LINEAR = 0, /* per column segment: v = alpha*(acc+bias) [+ res]; w = [accin +] beta*v;
+  QVC_EPI_LINEAR = 0, /* per column segment: v = alpha*(acc+bias) [+ res | res_op]; w = [accin +] beta*v;
                          raw <- w ; op <- round(leaky_relu(w, slope))                          */
   QVC_EPI_GATE = 1,   /* WN gate (modules.py:14-34): cout = 2H; op[n] <- round(tanh(a[n]) *
                          sigmoid(a[n+H])), a = acc + bias                                      */
@@ -86,6 +86,12 @@ typedef struct {
   float      slope;         /* leaky-relu slope applied to the operand copy (1 = identity)     */
   int32_t    _pad;
   qvc_tensor res;           /* fp32, optional (ptr NULL = absent)                              */
+  qvc_tensor res_op;        /* alternative to `res`: the residual given as an operand-format tensor that
+                               holds leaky_relu(r, s); it is undone with r = v > 0 ? v : v * res_inv_slope
+                               (res_inv_slope = 1/s).  Lets a residual stream live only as the operand
+                               copy the next convolution reads anyway.                          */
+  float      res_inv_slope;
+  int32_t    _pad2;
   qvc_tensor accin;         /* fp32, optional                                                  */
   qvc_tensor raw;           /* fp32 out, optional                                              */
   qvc_tensor op;            /* operand-format out, optional                                    */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libqvc_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-QVC_ABI_VERSION = 2
+QVC_ABI_VERSION = 3
 QVC_NUM_LAYERS = 114
 
 OPF_F32, OPF_TF32, OPF_BF16 = 0, 1, 2
@@ -32,7 +32,8 @@ class Tensor(C.Structure):
 class EpiSegment(C.Structure):
     _fields_ = [("col0", C.c_int32), ("ncols", C.c_int32), ("alpha", C.c_float), ("beta", C.c_float),
                 ("slope", C.c_float), ("_pad", C.c_int32),
-                ("res", Tensor), ("accin", Tensor), ("raw", Tensor), ("op", Tensor)]
+                ("res", Tensor), ("res_op", Tensor), ("res_inv_slope", C.c_float), ("_pad2", C.c_int32),
+                ("accin", Tensor), ("raw", Tensor), ("op", Tensor)]
 
 
 class ConvArgs(C.Structure):

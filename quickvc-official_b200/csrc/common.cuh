@@ -96,7 +96,8 @@ struct TRef {
 struct EpiSeg {
   int32_t col0, ncols;
   float alpha, beta, slope;
-  TRef res, accin, raw, op;
+  float res_inv_slope;
+  TRef res, res_op, accin, raw, op;
 };
 
 struct EpiParams {
@@ -202,6 +203,13 @@ __device__ __forceinline__ void epi_linear(const EpiParams& ep, int b, int t, in
       load_f32<VEC>(sg.res.at<float>(b, t, c), r);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) v[i] += r[i];
+    } else if (sg.res_op.present()) {
+      const OT* rp = sg.res_op.at<OT>(b, t, c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float r = op_to_float(rp[i]);
+        v[i] += r > 0.f ? r : r * sg.res_inv_slope;
+      }
     }
     if (sg.accin.present()) {
       float r[VEC];

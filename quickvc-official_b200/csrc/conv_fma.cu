@@ -144,9 +144,12 @@ int build_epi_params(const qvc_conv_args& a, EpiParams* ep) {
     EpiSeg& d = ep->seg[s];
     d.col0 = g.col0; d.ncols = g.ncols; d.alpha = g.alpha; d.beta = g.beta; d.slope = g.slope;
     d.res = make_tref(g.res); d.accin = make_tref(g.accin); d.raw = make_tref(g.raw); d.op = make_tref(g.op);
+    d.res_op = make_tref(g.res_op); d.res_inv_slope = g.res_inv_slope;
+    if (s < ep->nseg && a.epilogue == QVC_EPI_LINEAR)
+      QVC_REQUIRE(!(g.res.ptr && g.res_op.ptr), "conv1d: segment %d has both res and res_op", s);
     if (s < ep->nseg && a.epilogue == QVC_EPI_LINEAR) {
       QVC_REQUIRE(g.col0 % 8 == 0 && g.ncols % 8 == 0, "conv1d: segment %d not 8-column aligned", s);
-      const qvc_tensor* ts[4] = {&g.res, &g.accin, &g.raw, &g.op};
+      const qvc_tensor* ts[5] = {&g.res, &g.accin, &g.raw, &g.op, &g.res_op};
       for (const qvc_tensor* t : ts)
         if (t->ptr) QVC_REQUIRE(t->ld % 8 == 0 && t->bstride % 8 == 0 && ((uintptr_t)t->ptr & 15) == 0,
                                 "conv1d: epilogue tensor of segment %d not 8-element / 16-byte aligned", s);

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         bool primed = false;
         if (context(0, k)) {
           const int nv = frames_at(col_begin);
-          if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
+          if (nv > 0) lin_load<OPF>(k, t0 + col_begin, nv, r);
           primed = true;
         }
         mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           for (int col = col_begin; col < col_end; col += 64) {
             const int nv = frames_at(col);
             if (nv <= 0) break;
-            if (!(primed && ci == 0 && col == col_begin)) lin_load(k, t0 + col, nv, r);
+            if (!(primed && ci == 0 && col == col_begin)) lin_load<OPF>(k, t0 + col, nv, r);
             lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)(ci * N + col));
           }
         }

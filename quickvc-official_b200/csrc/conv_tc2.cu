@@ -256,7 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         bool primed = false;
         if (warp_live) {
           const int nv = frames_at(col_begin);
-          if (nv > 0) lin_load(k, t0 + col_begin, nv, r);
+          if (nv > 0) lin_load<OPF>(k, t0 + col_begin, nv, r);
           primed = true;
         }
         mbar_wait(tmem_full + 8 * buf, bph);
@@ -265,7 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           for (int col = col_begin; col < col_end; col += 64) {
             const int nv = frames_at(col);
             if (nv <= 0) break;
-            if (!(primed && col == col_begin)) lin_load(k, t0 + col, nv, r);
+            if (!(primed && col == col_begin)) lin_load<OPF>(k, t0 + col, nv, r);
             lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)col);
           }
         }

@@ -170,16 +170,43 @@ struct LinCtx {
   float bias;
 };
 
-// loads only: the residual if the segment has one, else the accumulate-into tensor (else nothing)
+// loads only: the residual if the segment has one (fp32, or the operand-format copy -- kept as raw bits here, decoded
+// in lin_finish so that nothing waits for the loads), else the accumulate-into tensor (else nothing)
+template <int OPF>
 __device__ __forceinline__ void lin_load(const LinCtx& k, int t, int nv, float* r) {
   const EpiSeg& sg = *k.sg;
+  if (sg.res_op.present()) {
+    using OT = typename OpType<OPF>::type;
+    const OT* rp = sg.res_op.at<OT>(k.b, t, k.c);
+    const int ld = sg.res_op.ld;
+    if constexpr (OPF == QVC_OPF_BF16) {
+      const uint16_t* rp16 = reinterpret_cast<const uint16_t*>(rp);
+      if (k.all_ok && nv == 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) r[i] = __uint_as_float((uint32_t)rp16[i * ld]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) r[i] = (k.ok && i < nv) ? __uint_as_float((uint32_t)rp16[i * ld]) : 0.f;
+      }
+    } else {
+      const float* rpf = reinterpret_cast<const float*>(rp);
+      if (k.all_ok && nv == 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) r[i] = rpf[i * ld];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) r[i] = (k.ok && i < nv) ? rpf[i * ld] : 0.f;
+      }
+    }
+    return;
+  }
   const TRef& src = sg.res.present() ? sg.res : sg.accin;
   if (!src.present()) return;
   const float* rp = src.at<float>(k.b, t, k.c);
   const int ld = src.ld;
   if (k.all_ok && nv == 64) {
     // common case, no per-element predicate: one IMAD.WIDE + LDG per element (the predicated form costs
-    // ~9 instructions per load and made this epilogue issue-bound, profiles/r01_conv_tc_notes.md)
+    // ~9 instructions per load and made this epilogue issue-bound, profiles/r01_v2_summary.md)
 #pragma unroll
     for (int i = 0; i < 64; ++i) r[i] = rp[i * ld];
   } else {
@@ -189,10 +216,11 @@ __device__ __forceinline__ void lin_load(const LinCtx& k, int t, int nv, float* 
 }
 
 template <int OPF>
-__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, const float* r, uint32_t taddr) {
+__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float* r, uint32_t taddr) {
   using OT = typename OpType<OPF>::type;
   const EpiSeg& sg = *k.sg;
-  const bool has_res = sg.res.present(), has_acc = sg.accin.present();
+  const bool res_from_op = sg.res_op.present();
+  const bool has_res = sg.res.present() || res_from_op, has_acc = sg.accin.present();
   const float alpha = sg.alpha, beta = sg.beta, slope = sg.slope;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -201,6 +229,16 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, const
     float v[32];
     tmem_ld32(taddr + 32 * h, v);
     tmem_wait();
+    float* rr = r + 32 * h;
+    if (res_from_op) {                               // decode the operand copy in place: undo the leaky-relu
+      const float inv = sg.res_inv_slope;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = rr[i];
+        if constexpr (OPF == QVC_OPF_BF16) x = __uint_as_float(__float_as_uint(x) << 16);
+        rr[i] = x > 0.f ? x : x * inv;
+      }
+    }
     if (has_res && has_acc) {
       // both streams (last convolution of MRF blocks 2 and 3): the accumulate-into tensor is loaded late, 8 at a time
       const float* ap = sg.accin.at<float>(k.b, th, k.c);
@@ -211,15 +249,15 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, const
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = (k.ok && g + i < nvh) ? ap[(g + i) * ld] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, r[32 * h + g + i]), a[i]);
+        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, rr[g + i]), a[i]);
       }
     } else if (has_res) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, r[32 * h + i]);
+      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, rr[i]);
     } else if (has_acc) {
       const float ab = alpha * beta;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaf(ab, v[i] + k.bias, r[32 * h + i]);
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(ab, v[i] + k.bias, rr[i]);
     } else {
       const float ab = alpha * beta;
 #pragma unroll

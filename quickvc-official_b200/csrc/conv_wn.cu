@@ -354,13 +354,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
       int nv = p.out_rows - (t0 + col);
       nv = nv < 0 ? 0 : (nv > HN ? HN : nv);
       float r[64];
-      if (live[0] && nv > 0) lin_load(kx[0], t0 + col, nv, r);           // in flight before the accumulator is complete
+      if (live[0] && nv > 0) lin_load<OPF>(kx[0], t0 + col, nv, r);           // in flight before the accumulator is complete
       mbar_wait(acc2_full, par);
       tc_fence_after();
       if (nv > 0) {
         if (live[0]) lin_finish<OPF>(kx[0], t0 + col, nv, r, tlane + (uint32_t)(2 * PN + col));
         if (live[1]) {
-          lin_load(kx[1], t0 + col, nv, r);
+          lin_load<OPF>(kx[1], t0 + col, nv, r);
           lin_finish<OPF>(kx[1], t0 + col, nv, r, tlane + (uint32_t)(3 * PN + col));
         }
       }

@@ -8,6 +8,8 @@
 // Whole-batch buffers serve the prior encoder and the flow (192 channels at the unit frame rate);
 // the decoder runs per sub-batch of `chunk_utts` utterances (default: the whole batch, bounded only by
 // the workspace size).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "engine.h"
 
@@ -121,6 +123,17 @@ qvc_conv_args layer_args(const Ctx& c, int li, qvc_tensor x, int batch, int x_ro
 
 int run(const Ctx& c, const qvc_conv_args& a) { return qvc_conv1d(&a, (qvc_stream_t)c.st); }
 
+// bf16 mode on the tensor-core back end keeps the residual streams of the MRF only as the operand copy the next
+// convolution reads anyway (qvc_epi_segment.res_op): the c2 layers are memory-bound there and this halves their
+// traffic.  In the fp32 (TF32) mode the residual streams stay unrounded fp32.
+bool residual_from_operand(const Ctx& c) {
+  static const bool enabled = [] {
+    const char* e = getenv("QVC_RES_FROM_OP");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && c.m->opformat == QVC_OPF_BF16 && c.m->backend == QVC_BACKEND_TCGEN05;
+}
+
 // One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack
 // input; on return skipO holds the operand copy of the summed skip output.
 int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, int n_layers,
@@ -172,6 +185,7 @@ int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, in
 int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void* x1O, void* tO,
             float* xaR, void* xaO, float* sumR, qvc_tensor final_op, float final_slope, float* final_raw) {
   const int64_t bs = (int64_t)rows * ch;
+  const bool rfo = residual_from_operand(c);
   for (int r = 0; r < 3; ++r) {
     const int lb = l_res0 + 6 * r;
     const float* srcR = x1R;
@@ -185,9 +199,14 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
 
       qvc_conv_args d = layer_args(c, lb + 3 + j, tens(tO, bs, ch), cb, rows, rows);
       d.seg[0] = seg(0, ch);
-      d.seg[0].res = tens(srcR, bs, ch);
+      if (rfo) {
+        d.seg[0].res_op = tens(srcO, bs, ch);       // leaky_relu(x, 0.1) in operand format
+        d.seg[0].res_inv_slope = 10.f;
+      } else {
+        d.seg[0].res = tens(srcR, bs, ch);
+      }
       if (j < 2) {
-        d.seg[0].raw = tens(xaR, bs, ch);
+        if (!rfo) d.seg[0].raw = tens(xaR, bs, ch);
         d.seg[0].op = tens(xaO, bs, ch);
         d.seg[0].slope = 0.1f;
         srcR = xaR; srcO = xaO;
@@ -235,7 +254,7 @@ int run_decoder(const Ctx& c, const Buffers& bf, const Shapes& s, const void* zO
       qvc_conv_args a = layer_args(c, L_UPS + 0, tens(bf.aO, (int64_t)T * C_PRE, C_PRE), cb, T, T);
       a.seg[0] = seg(0, UP0 * C_UP0);
       a.seg[0].slope = 0.1f;
-      a.seg[0].raw = tens(bf.x1R, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
+      if (!residual_from_operand(c) || (taps && taps->ups0)) a.seg[0].raw = tens(bf.x1R, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
       a.seg[0].op = tens(bf.x1O, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
       QVC_PROPAGATE(run(c, a));
       if (taps && taps->ups0)
@@ -255,7 +274,7 @@ int run_decoder(const Ctx& c, const Buffers& bf, const Shapes& s, const void* zO
       qvc_conv_args a = layer_args(c, L_UPS + 1, tens(bf.uO, (int64_t)R0 * C_UP0, C_UP0), cb, R0, R0);
       a.seg[0] = seg(0, UP1 * C_UP1);
       a.seg[0].slope = 0.1f;
-      a.seg[0].raw = tens(bf.y1R, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
+      if (!residual_from_operand(c) || (taps && taps->ups1)) a.seg[0].raw = tens(bf.y1R, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
       a.seg[0].op = tens(bf.y1O, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
       QVC_PROPAGATE(run(c, a));
       if (taps && taps->ups1)

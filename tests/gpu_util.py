@@ -46,6 +46,7 @@ def make_args(x, w, bias, *, k, dil, pad_left, out_rows, opf, backend, epilogue=
         g.col0, g.ncols = s["col0"], s["ncols"]
         g.alpha, g.beta, g.slope = s.get("alpha", 1.0), s.get("beta", 1.0), s.get("slope", 1.0)
         g.res, g.accin, g.raw, g.op = (tref(s.get(n)) for n in ("res", "accin", "raw", "op"))
+        g.res_op, g.res_inv_slope = tref(s.get("res_op")), s.get("res_inv_slope", 1.0)
     a.noise, a.aux0, a.aux1 = tref(noise), tref(aux0), tref(aux1)
     a.opformat, a.backend = opf, backend
     return a

@@ -71,6 +71,28 @@ def test_conv_linear(geom, be):
 
 
 @pytest.mark.parametrize("be", BACKENDS, ids=IDS)
+@pytest.mark.parametrize("geom", [(2, 300, 128, 128, 3), (1, 700, 256, 256, 7)], ids=["128ch", "256ch-pairs"])
+def test_conv_residual_from_operand_copy(be, geom):
+    """seg.res_op: the residual given as the operand-format copy of leaky_relu(r, 0.1)."""
+    _, backend, opf = be
+    B, rows, cin, cout, k = geom
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = to_op(torch.randn(B, rows, cin, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(cout, k, cin, generator=g) / (cin * k) ** 0.5, opf).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    r = torch.randn(B, rows, cout, generator=g)
+    r_op = to_op(torch.where(r > 0, r, 0.1 * r), opf).to(DEV)            # what a producing epilogue stores
+    raw = torch.full((B, rows, cout), float("nan"), device=DEV)
+    conv1d(x, w, bias, k=k, dil=1, pad_left=(k - 1) // 2, out_rows=rows, opf=opf, backend=backend,
+           segs=[dict(col0=0, ncols=cout, res_op=r_op, res_inv_slope=10.0, raw=raw)])
+    torch.cuda.synchronize()
+    acc = ref_conv(x.cpu().float(), w.cpu().float(), k, 1, (k - 1) // 2, rows)
+    rq = r_op.cpu().double()
+    want = acc + bias.cpu().double() + torch.where(rq > 0, rq, rq * 10.0)
+    assert float((raw.cpu().double() - want).abs().max()) < _tol(opf) * float(want.abs().max())
+
+
+@pytest.mark.parametrize("be", BACKENDS, ids=IDS)
 def test_conv_two_segments_wn_res_skip(be):
     _, backend, opf = be
     B, rows, H = 2, 70, 192
