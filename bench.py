@@ -386,6 +386,24 @@ def run_ours(args, rank, local_rank, world):
             line[name] = latency(lambda: net.infer(u1, m5, noise=n1))
             line[name]["cached_speaker"] = latency(lambda: net.infer_with_embedding(u1, emb, noise=n1))
 
+        # SURVEY.md section 8f "next" #1: the target-mel front end (wave_to_mel, convert.py:75-77) for one 10 s target
+        from quickvc_official_b200 import mel as qmel
+        from oracle import mel_oracle
+        margs = (1280, 80, 16000, 320, 1280, 0.0, None)
+        wav_h = (torch.rand(1, 160000) * 2 - 1) * 0.5
+        wav = wav_h.to(dev)
+        ms_mel, _ = timed(lambda: qmel.wave_to_mel(wav, *margs), 20, 3)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            mel_oracle.wave_to_mel(wav_h, *margs)
+        cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+        stft_flops = 2.0 * 500 * 1280 * 1296
+        line["mel_frontend"] = {"ms": ms_mel, "audio_s_per_s": 10.0 / (ms_mel * 1e-3), "cpu_oracle_ms": cpu_ms,
+                                "stft_gemm_tflops": stft_flops / (ms_mel * 1e-3) / 1e12,
+                                "note": "wave_to_mel of one 10 s target utterance (B=1): reflect pad + STFT as an exact-fp32 FMA "
+                                        "GEMM (1.66 GFLOP) + magnitude + Slaney mel + log; latency bound (500 frames); CPU = "
+                                        "torch.stft oracle on the host threads"}
+
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         sample = max(1, args.cpu_sample_batch)

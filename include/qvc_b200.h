@@ -162,6 +162,25 @@ int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm, int tm, fl
                   void* workspace, size_t workspace_bytes, qvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Target-mel front end: wave_to_mel (mel_processing.py:15-98, called at convert.py:75-77) -- the step right
+ * before the path; SURVEY.md section 8f "next" #1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* basis;     /* [rows16][n_fft] fp32: row r < bins = hann[n] cos(2 pi r n / n_fft), row bins + r =
+                             -hann[n] sin(...), zero rows up to rows16 = round_up(2 bins, 16); bins = n_fft/2+1 */
+  const float* fbank_t;   /* [bins][n_mels] fp32: the mel filterbank, transposed                              */
+  int32_t n_fft, hop, n_mels, _pad;
+} qvc_mel_weights;
+
+/* frames produced for `samples` input samples: 1 + (samples + (n_fft - hop) - n_fft) / hop */
+int qvc_mel_frames(const qvc_mel_weights* w, int samples);
+size_t qvc_mel_workspace_bytes(const qvc_mel_weights* w, int batch, int samples);
+/* wave (B, samples) fp32 -> mel (B, n_mels, frames) fp32 = log(max(fbank . sqrt(|STFT|^2 + 1e-6), 1e-5)), with the
+ * reference's reflect padding of (n_fft - hop)/2 samples on both sides and center=False. */
+int qvc_wave_to_mel(const qvc_mel_weights* w, const float* wave, int batch, int samples, float* mel,
+                    void* workspace, size_t workspace_bytes, qvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Tail: magnitude exp / phase pi*sin, 16-point inverse real DFT, Hann window, hop-4 overlap-add,
  * envelope division and trim (torch.istft as called at models.py:350,399-401), then the x4
  * zero-stuffing and the learnable 4->1 synthesis filter (models.py:404-406), fused.

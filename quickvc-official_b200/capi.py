@@ -52,6 +52,11 @@ class SpkWeights(C.Structure):
                 ("lin_w", C.c_void_p), ("lin_b", C.c_void_p)]
 
 
+class MelWeights(C.Structure):
+    _fields_ = [("basis", C.c_void_p), ("fbank_t", C.c_void_p), ("n_fft", C.c_int32), ("hop", C.c_int32),
+                ("n_mels", C.c_int32), ("_pad", C.c_int32)]
+
+
 class TailWeights(C.Structure):
     _fields_ = [("window", C.c_void_p), ("synth", C.c_void_p), ("window_host", C.c_void_p), ("synth_host", C.c_void_p)]
 
@@ -85,6 +90,10 @@ SYMBOLS = {
     "qvc_spk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "qvc_spk_embed": (C.c_int, [C.POINTER(SpkWeights), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),
+    "qvc_mel_frames": (C.c_int, [C.POINTER(MelWeights), C.c_int]),
+    "qvc_mel_workspace_bytes": (C.c_size_t, [C.POINTER(MelWeights), C.c_int, C.c_int]),
+    "qvc_wave_to_mel": (C.c_int, [C.POINTER(MelWeights), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]),
     "qvc_tail": (C.c_int, [C.POINTER(TailWeights), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
     "qvc_infer_workspace_bytes": (C.c_size_t, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int]),
