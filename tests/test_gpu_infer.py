@@ -167,3 +167,22 @@ def test_pair_kernels_on_the_golden_case(precision, sd, model_cfg, monkeypatch):
     before = capi.launch_count()
     net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
     assert capi.launch_count() - before > forced          # the fused WN layers save one launch each
+
+
+@pytest.mark.parametrize("force_pairs", [False, True], ids=["auto", "pairs"])
+@pytest.mark.parametrize("shape", [(3, 1, 1, 130), (1, 7, 1, 64), (2, 513, 1, 300), (5, 129, 5, 128)],
+                         ids=["T1", "T7_shortmel", "T513_ragged", "T129_mel128x5"])
+def test_odd_shapes_against_oracle(shape, force_pairs, sd, model_cfg, monkeypatch):
+    """Ragged and degenerate sizes through every tiling decision (single frame, fewer frames than filter taps, one frame
+    past a tile boundary, per-utterance mels), with the CTA-pair kernels forced on as well."""
+    if force_pairs:
+        monkeypatch.setenv("QVC_TC_2CTA_FORCE", "1")
+    b, t, bm, tm = shape
+    unit, mel, noise = synth.synthetic_inputs(b, t, bm, tm, 3)
+    ref = qvc_oracle.infer(sd, unit, mel, noise)
+    for precision in ("tf32", "bf16"):
+        net = get_net(sd, model_cfg, precision, "tcgen05")
+        wave = net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
+        torch.cuda.synchronize()
+        assert wave.shape == ref.shape
+        assert synth.max_abs(wave, ref) < MODES[(precision, "tcgen05")][0], precision
