@@ -295,6 +295,18 @@ def run_ours(args, rank, local_rank, world):
     achieved = conv_flops / (conv_ms_step * 1e-3) / 1e12
     tf32 = args.precision != "bf16"
     peak = pk["bf16_sustained"] * (0.5 if tf32 else 1.0)
+    peak_src = pk["source"] + ": bf16_tflops_sustained (kernels timed inside a long step)" + \
+        (" x 0.5 -- TF32 operands run at half the bf16 tensor rate" if tf32 else "")
+    tf32_path = os.path.join(ROOT, "profiles", "r01_tf32_peak.json")
+    if tf32 and os.path.exists(tf32_path):
+        # the TF32 denominator measured on this pool the way the driver measured the bf16 one (SURVEY.md section 8d
+        # leaves it to the builder): cuBLAS TF32 8192^3, sustained figure for kernels timed inside a long step
+        with open(tf32_path) as f:
+            tp = json.load(f)
+        peak = tp["tf32_tflops_sustained"]
+        peak_src = ("measured (profiles/r01_tf32_peak.json, scripts/measure_tf32_peak.py): cuBLAS TF32 8192^3 sustained "
+                    f"{tp['tf32_tflops_sustained']:.1f} TFLOP/s (burst {tp['tf32_tflops']:.1f}); half of MEASURED_PEAKS.json's "
+                    f"bf16 sustained would be {pk['bf16_sustained'] * 0.5:.1f}")
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.precision == "tf32" and B == 64 and T == 500:
@@ -309,8 +321,8 @@ def run_ours(args, rank, local_rank, world):
         "launches_per_step": int(conv_launches), "avg_launch_us": conv_ms_step * 1e3 / max(1, conv_launches),
         "kernel_ms_per_step": conv_ms_step, "kernel_share_of_step": conv_ms_step / ms,
         "flops_per_step": conv_flops,
-        "peak_source": pk["source"] + ": bf16_tflops_sustained (kernels timed inside a long step)"
-                       + (" x 0.5 -- TF32 operands run at half the bf16 tensor rate and no TF32 figure is measured" if tf32 else ""),
+        "peak_source": peak_src,
+        "frac_of_half_bf16_sustained": achieved / (pk["bf16_sustained"] * 0.5) if tf32 else None,
         "frac_of_bf16_sustained": achieved / pk["bf16_sustained"],
         "whole_step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / 1e12 / peak, "flops": flops},
         "note": "algorithmic FLOPs (207.2 MFLOP per unit frame per utterance, SURVEY.md section 8d) over CUDA-event launch "
