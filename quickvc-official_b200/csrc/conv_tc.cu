@@ -370,7 +370,15 @@ int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream
 }  // namespace
 
 EncodeTiledFn tc_get_encode() { return get_encode(); }
-int tc_sm_count() { return sm_count(); }
+// SMs the persistent convolution grids leave free (per host thread): while the speaker encoder's cluster runs on its
+// side stream, a grid of one CTA per SM would leave 8 CTAs waiting for it -- with static tile assignment their tiles
+// would finish ~0.5 ms late (measured: +0.45 ms per step tf32, +0.65 ms bf16, scripts/spk_overlap.py).
+thread_local int g_reserved_sms = 0;
+void tc_reserve_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+int tc_sm_count() {
+  const int n = sm_count() - g_reserved_sms;
+  return n < 2 ? 2 : n;
+}
 int tc_env_int(const char* name, int dflt) { return env_int(name, dflt); }
 bool tc_prof_next(cudaEvent_t* e0, cudaEvent_t* e1) { return prof_next(e0, e1); }
 
@@ -508,7 +516,7 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
   }
 
-  int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+  int grid = p.ntiles < tc_sm_count() ? p.ntiles : tc_sm_count();
   const int grid_env = env_int("QVC_TC_GRID", 0);
   if (grid_env >= 1 && grid_env < grid) grid = grid_env;
 #define QVC_TC_DISPATCH(OPF)                                                                         \

@@ -393,7 +393,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tc_get_encode();
-int tc_sm_count();
+int tc_sm_count();                  // SMs available to a persistent convolution grid (minus tc_reserve_sms)
+void tc_reserve_sms(int n);         // per host thread; see conv_tc.cu
 int tc_env_int(const char* name, int dflt);
 bool tc_prof_next(cudaEvent_t* e0, cudaEvent_t* e1);
 int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream);     // conv_tc2.cu; QVC_ERR_UNSUPPORTED = not applicable

@@ -416,9 +416,21 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
   QVC_PROPAGATE(cond_vectors(m->cond_w, m->cond_b, g, n_embed, m->cond_rows, bf.condvec, gst));
   if (side) QVC_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
   const int64_t cond_bs = n_embed > 1 ? m->cond_rows : 0;
+  // the prior encoder runs beside the speaker encoder: leave its cluster(s) of 8 SMs out of the convolution grids
+  struct Reserve {
+    explicit Reserve(int n) { tc_reserve_sms(n); }
+    ~Reserve() { tc_reserve_sms(0); }
+  };
+  int spk_sms = 0;
+  if (with_spk) {
+    const int nseq = mel_frames > 128 ? (mel_frames - 128 + 63) / 64 + 1 : mel_batch;
+    spk_sms = 8 * ((nseq + 1) / 2);                 // lstm.cu: two sequences per 8-CTA cluster
+    if (spk_sms > 64) spk_sms = 64;
+  }
 
   // prior encoder enc_p (models.py:75-95)
   {
+    Reserve reserve(spk_sms);
     qvc_conv_args a = layer_args(c, L_ENC_PRE, tens(bf.unitO, (int64_t)T * UNIT_CH, UNIT_CH), B, T, T);
     a.seg[0] = seg(0, HID);
     a.seg[0].raw = tens(bf.xR, bs, HID);

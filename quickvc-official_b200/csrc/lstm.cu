@@ -10,6 +10,8 @@
 // 2.4 % of the path's FLOPs.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -31,6 +33,7 @@ struct RecParams {
   const float* w_hh;      // (1024, 256)
   const float* gx;        // [rows][1024] input projection (bias included)
   int32_t nseq, steps;
+  int32_t spc;            // sequences per cluster (<= MAXSEQ): fewer = more clusters, shorter steps
   int32_t row_stride;     // first gx row of sequence s is s*row_stride ...
   int32_t last_row;       // ... except, when >= 0, the last sequence starts here
   float* hseq;            // [nseq][steps][256] or NULL
@@ -46,8 +49,8 @@ lstm_recurrent_kernel(const RecParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int group = blockIdx.x / CLUSTER;                   // which block of <= 8 sequences
-  const int s_base = group * MAXSEQ;
-  const int ns = min(MAXSEQ, p.nseq - s_base);
+  const int s_base = group * p.spc;
+  const int ns = min(p.spc, p.nseq - s_base);
   const int tid = threadIdx.x;
   const int ks = tid & 7;                                   // k-slice / sequence owned in the update
   const int u = tid >> 3;                                   // local hidden unit
@@ -291,7 +294,14 @@ extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm,
     rp.last_row = layer == 0 ? pl.last_row : -1;
     rp.hseq = layer < 2 ? hseq : nullptr;
     rp.hlast = layer == 2 ? hlast : nullptr;
-    const int groups = (pl.nseq + MAXSEQ - 1) / MAXSEQ;
+    // Sequences (windows) are independent: spreading them over more clusters shortens every one of the 384
+    // dependent steps (per-step FMA work is proportional to the sequences of a cluster).  Default 2 per cluster:
+    // one 10 s target mel = 7 windows = 4 clusters = 32 SMs for ~0.9 ms instead of 8 SMs for 1.7 ms, which keeps the
+    // encoder off the critical path of the step (it runs beside the prior encoder and the flow waits for it).
+    int spc = 2;
+    if (const char* e = getenv("QVC_SPK_SPC")) { const int v = atoi(e); if (v >= 1 && v <= MAXSEQ) spc = v; }
+    rp.spc = spc;
+    const int groups = (pl.nseq + spc - 1) / spc;
     lstm_recurrent_kernel<<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp);
     QVC_PROPAGATE(post_launch("lstm_recurrent_kernel"));
   }
