@@ -166,45 +166,47 @@ lstm_recurrent_kernel(const RecParams p) {
   }
 }
 
-// embed[e][n] = mean_w normalise(relu(lin_w h[w] + lin_b))   (models.py:517-518, 540)
-__global__ void __launch_bounds__(HID) spk_finish_kernel(const float* hlast, const float* lin_w,
-                                                         const float* lin_b, int seq_per_embed,
-                                                         float* g_out) {
+// emb[w][n] = normalise(relu(lin_w h[w] + lin_b))   (models.py:517-518): one CTA per window
+__global__ void __launch_bounds__(HID) spk_project_kernel(const float* hlast, const float* lin_w, const float* lin_b,
+                                                          float* emb) {
   __shared__ float hs[HID];
   __shared__ float red[HID / 32];
+  const int w = blockIdx.x, n = threadIdx.x;
+  hs[n] = hlast[(int64_t)w * HID + n];
+  __syncthreads();
+  float a = lin_b[n];
+  const float4* wr = reinterpret_cast<const float4*>(lin_w + (int64_t)n * HID);
+#pragma unroll 4
+  for (int k4 = 0; k4 < HID / 4; ++k4) {
+    const float4 wv = __ldg(wr + k4);
+    a = fmaf(wv.x, hs[4 * k4], a);
+    a = fmaf(wv.y, hs[4 * k4 + 1], a);
+    a = fmaf(wv.z, hs[4 * k4 + 2], a);
+    a = fmaf(wv.w, hs[4 * k4 + 3], a);
+  }
+  a = fmaxf(a, 0.f);
+  float sq = a * a;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((n & 31) == 0) red[n >> 5] = sq;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < HID / 32; ++i) tot += red[i];
+  emb[(int64_t)w * HID + n] = a / sqrtf(tot);
+}
+
+// g[e][n] = mean over the windows of embedding e, summed in window order (models.py:540): deterministic
+__global__ void __launch_bounds__(HID) spk_mean_kernel(const float* emb, int seq_per_embed, float* g_out) {
   const int e = blockIdx.x, n = threadIdx.x;
   float mean = 0.f;
-  for (int w = 0; w < seq_per_embed; ++w) {
-    __syncthreads();
-    hs[n] = hlast[((int64_t)e * seq_per_embed + w) * HID + n];
-    __syncthreads();
-    float a = lin_b[n];
-    const float4* wr = reinterpret_cast<const float4*>(lin_w + (int64_t)n * HID);
-#pragma unroll 4
-    for (int k4 = 0; k4 < HID / 4; ++k4) {
-      const float4 wv = __ldg(wr + k4);
-      a = fmaf(wv.x, hs[4 * k4], a);
-      a = fmaf(wv.y, hs[4 * k4 + 1], a);
-      a = fmaf(wv.z, hs[4 * k4 + 2], a);
-      a = fmaf(wv.w, hs[4 * k4 + 3], a);
-    }
-    a = fmaxf(a, 0.f);
-    float sq = a * a;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((n & 31) == 0) red[n >> 5] = sq;
-    __syncthreads();
-    float tot = 0.f;
-#pragma unroll
-    for (int i = 0; i < HID / 32; ++i) tot += red[i];
-    mean += a / sqrtf(tot);
-  }
+  for (int w = 0; w < seq_per_embed; ++w) mean += emb[((int64_t)e * seq_per_embed + w) * HID + n];
   g_out[(int64_t)e * HID + n] = mean / (float)seq_per_embed;
 }
 
 struct SpkPlan {
   int nseq, steps, n_embed, seq_per_embed, row_stride, last_row;
-  size_t off_mel, off_gx, off_hseq, off_hlast, total;
+  size_t off_mel, off_gx, off_hseq, off_hlast, off_emb, total;
 };
 
 SpkPlan make_plan(int bm, int tm) {
@@ -231,6 +233,7 @@ SpkPlan make_plan(int bm, int tm) {
   pl.off_gx = o;    o += up(gx_rows * GATES * 4);
   pl.off_hseq = o;  o += up((size_t)pl.nseq * pl.steps * HID * 4);
   pl.off_hlast = o; o += up((size_t)pl.nseq * HID * 4);
+  pl.off_emb = o;   o += up((size_t)pl.nseq * HID * 4);
   pl.total = o;
   return pl;
 }
@@ -305,6 +308,9 @@ extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm,
     lstm_recurrent_kernel<<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp);
     QVC_PROPAGATE(post_launch("lstm_recurrent_kernel"));
   }
-  spk_finish_kernel<<<pl.n_embed, HID, 0, stream>>>(hlast, w->lin_w, w->lin_b, pl.seq_per_embed, g_out);
-  return post_launch("spk_finish_kernel");
+  float* emb = reinterpret_cast<float*>(ws + pl.off_emb);
+  spk_project_kernel<<<pl.nseq, HID, 0, stream>>>(hlast, w->lin_w, w->lin_b, emb);
+  QVC_PROPAGATE(post_launch("spk_project_kernel"));
+  spk_mean_kernel<<<pl.n_embed, HID, 0, stream>>>(emb, pl.seq_per_embed, g_out);
+  return post_launch("spk_mean_kernel");
 }
