@@ -360,7 +360,7 @@ def run_ours(args, rank, local_rank, world):
         model = net._engine._ensure_model(dev)
         stream = torch.cuda.current_stream().cuda_stream
         ms_tail, _ = timed(lambda: capi.check(lib.qvc_tail(C.byref(model.tail), post.data_ptr(), 72, B, frames_post,
-                                                           wave.data_ptr(), None, stream), "qvc_tail"), 20, 3)
+                                                           None, 0, wave.data_ptr(), None, stream), "qvc_tail"), 20, 3)
         tail_bytes = B * frames_post * TAIL_BYTES_PER_POST_FRAME
         line["tail_roofline"] = {"bound": "hbm", "achieved": tail_bytes / (ms_tail * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": tail_bytes / (ms_tail * 1e-3) / 1e9 / pk["hbm"],

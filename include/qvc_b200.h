@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QVC_ABI_VERSION 3
+#define QVC_ABI_VERSION 4
 
 typedef struct CUstream_st* qvc_stream_t;   /* == cudaStream_t */
 
@@ -118,6 +118,13 @@ typedef struct {
   qvc_tensor aux0, aux1;    /* SAMPLE: optional fp32 copies of m and logs                      */
   int32_t    opformat;      /* qvc_opformat of x, w and every `op` output                      */
   int32_t    backend;       /* qvc_backend                                                     */
+  /* Ragged batches (utterances of different lengths padded to out_rows): when live_units is non-NULL,
+   * utterance b has live_units[b] * live_mul live output rows, and every `op` output row at or past that
+   * count is written as ZERO -- exactly the zero "same" padding the next convolution would have seen at
+   * the end of that utterance alone.  fp32 outputs (raw, aux) past the count are unspecified. */
+  const int32_t* live_units; /* device, [batch], or NULL                                       */
+  int32_t    live_mul;
+  int32_t    _pad3;
 } qvc_conv_args;
 
 int qvc_conv1d(const qvc_conv_args* args, qvc_stream_t stream);
@@ -194,9 +201,11 @@ typedef struct {
 } qvc_tail_weights;
 
 /* post :: [B][frames][ld] fp32 with 72 live channels (band*18 + {0..8 log-mag, 9..17 phase});
- * wave :: (B, 1, 16*(frames-1)) fp32; y_mb (optional) :: (B, 4, 4*(frames-1)) fp32. */
+ * wave :: (B, 1, 16*(frames-1)) fp32; y_mb (optional) :: (B, 4, 4*(frames-1)) fp32.
+ * live_units (optional, device [B]): utterance b only has live_units[b] * frames_per_unit + 1 post-net frames;
+ * its waveform is what torch.istft and the synthesis filter give for that many frames, followed by zeros. */
 int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, int batch, int frames,
-             float* wave, float* y_mb, qvc_stream_t stream);
+             const int32_t* live_units, int frames_per_unit, float* wave, float* y_mb, qvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole path
@@ -262,16 +271,20 @@ size_t qvc_infer_workspace_bytes(const qvc_model* model, int batch, int frames, 
 /* unit (B,256,T), mel (Bm,80,Tm), noise (B,192,T) [the torch.randn_like draw of models.py:94],
  * wave (B,1,320T); all fp32 device pointers in the reference layout.
  * g_in (optional, [n_embed][256]): a cached speaker embedding; when non-NULL the speaker encoder
- * is skipped and mel may be NULL. */
+ * is skipped and mel may be NULL.
+ * lengths (optional, device int32 [B], 1 <= lengths[b] <= T): a ragged batch padded to T frames.  Utterance b
+ * then gets, in wave[b][0 .. 320*lengths[b]), exactly the samples a call with that utterance alone
+ * (batch 1, frames lengths[b]) produces, followed by zeros; the padding frames of unit / noise are ignored.
+ * The reference has no such argument: it converts one utterance per call (convert.py:59-86). */
 int qvc_infer(const qvc_model* model, const float* unit, const float* mel, const float* noise,
-              const float* g_in, int batch, int frames, int mel_batch, int mel_frames,
-              float* wave, const qvc_taps* taps, void* workspace, size_t workspace_bytes,
-              qvc_stream_t stream);
+              const float* g_in, const int32_t* lengths, int batch, int frames, int mel_batch,
+              int mel_frames, float* wave, const qvc_taps* taps, void* workspace,
+              size_t workspace_bytes, qvc_stream_t stream);
 
-/* Decoder only (BASELINE.json config 3): z (B,192,T) fp32, g [1|B][256] fp32. */
-int qvc_decode(const qvc_model* model, const float* z, const float* g, int g_batch, int batch,
-               int frames, float* wave, const qvc_taps* taps, void* workspace,
-               size_t workspace_bytes, qvc_stream_t stream);
+/* Decoder only (BASELINE.json config 3): z (B,192,T) fp32, g [1|B][256] fp32; lengths as for qvc_infer. */
+int qvc_decode(const qvc_model* model, const float* z, const float* g, int g_batch,
+               const int32_t* lengths, int batch, int frames, float* wave, const qvc_taps* taps,
+               void* workspace, size_t workspace_bytes, qvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Misc

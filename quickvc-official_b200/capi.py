@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libqvc_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-QVC_ABI_VERSION = 3
+QVC_ABI_VERSION = 4
 QVC_NUM_LAYERS = 114
 
 OPF_F32, OPF_TF32, OPF_BF16 = 0, 1, 2
@@ -44,7 +44,8 @@ class ConvArgs(C.Structure):
                 ("epilogue", C.c_int32), ("nseg", C.c_int32),
                 ("seg", EpiSegment * 2),
                 ("noise", Tensor), ("aux0", Tensor), ("aux1", Tensor),
-                ("opformat", C.c_int32), ("backend", C.c_int32)]
+                ("opformat", C.c_int32), ("backend", C.c_int32),
+                ("live_units", C.c_void_p), ("live_mul", C.c_int32), ("_pad3", C.c_int32)]
 
 
 class SpkWeights(C.Structure):
@@ -94,13 +95,13 @@ SYMBOLS = {
     "qvc_mel_workspace_bytes": (C.c_size_t, [C.POINTER(MelWeights), C.c_int, C.c_int]),
     "qvc_wave_to_mel": (C.c_int, [C.POINTER(MelWeights), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
-    "qvc_tail": (C.c_int, [C.POINTER(TailWeights), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                           C.c_void_p, C.c_void_p]),
+    "qvc_tail": (C.c_int, [C.POINTER(TailWeights), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "qvc_infer_workspace_bytes": (C.c_size_t, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int]),
-    "qvc_infer": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                            C.c_int, C.c_int, C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),
-    "qvc_decode": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                             C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qvc_infer": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qvc_decode": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                             C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),
     "qvc_last_error": (C.c_char_p, []),
     "qvc_abi_version": (C.c_int, []),
     "qvc_launch_count": (C.c_uint64, []),

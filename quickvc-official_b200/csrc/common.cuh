@@ -109,7 +109,14 @@ struct EpiParams {
   int64_t bias_bs;
   EpiSeg seg[2];
   TRef noise, aux0, aux1;
+  const int32_t* live;  // ragged batches: utterance b has live[b] * live_mul live rows (nullptr: all of them)
+  int32_t live_mul;
 };
+
+// rows of utterance b whose operand outputs are real; the rest are written as zero (qvc_conv_args.live_units)
+__device__ __forceinline__ int live_rows(const EpiParams& ep, int b) {
+  return ep.live ? ep.live[b] * ep.live_mul : 0x7fffffff;
+}
 
 inline TRef make_tref(const qvc_tensor& t) { return TRef{t.ptr, t.bstride, t.ld}; }
 
@@ -188,6 +195,7 @@ __device__ __forceinline__ void store_f32(float* dst, const float* v) {
 template <int OPF, int VEC>
 __device__ __forceinline__ void epi_linear(const EpiParams& ep, int b, int t, int n, const float* acc) {
   using OT = typename OpType<OPF>::type;
+  const bool live = t < live_rows(ep, b);
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (s >= ep.nseg) break;
@@ -224,7 +232,7 @@ __device__ __forceinline__ void epi_linear(const EpiParams& ep, int b, int t, in
     if (sg.op.present()) {
       float a[VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) a[i] = leaky(v[i], sg.slope);
+      for (int i = 0; i < VEC; ++i) a[i] = live ? leaky(v[i], sg.slope) : 0.f;
       store_operand<OPF, VEC>(sg.op.at<OT>(b, t, c), a);
     }
   }
@@ -245,7 +253,13 @@ __device__ __forceinline__ void epi_gate(const EpiParams& ep, int b, int t, int 
   }
   const EpiSeg& sg = ep.seg[0];
   if (sg.raw.present()) store_f32<VEC>(sg.raw.at<float>(b, t, n), a);
-  if (sg.op.present()) store_operand<OPF, VEC>(sg.op.at<OT>(b, t, n), a);
+  if (sg.op.present()) {
+    if (t >= live_rows(ep, b)) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) a[i] = 0.f;
+    }
+    store_operand<OPF, VEC>(sg.op.at<OT>(b, t, n), a);
+  }
 }
 
 template <int OPF, int VEC>
@@ -265,7 +279,13 @@ __device__ __forceinline__ void epi_sample(const EpiParams& ep, int b, int t, in
   if (ep.aux0.present()) store_f32<VEC>(ep.aux0.at<float>(b, t, n), m);
   if (ep.aux1.present()) store_f32<VEC>(ep.aux1.at<float>(b, t, n), lg);
   if (sg.raw.present()) store_f32<VEC>(sg.raw.at<float>(b, t, n), z);
-  if (sg.op.present()) store_operand<OPF, VEC>(sg.op.at<OT>(b, t, n), z);
+  if (sg.op.present()) {
+    if (t >= live_rows(ep, b)) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) z[i] = 0.f;
+    }
+    store_operand<OPF, VEC>(sg.op.at<OT>(b, t, n), z);
+  }
 }
 
 // host-side translation of the public argument struct

@@ -131,6 +131,9 @@ int build_epi_params(const qvc_conv_args& a, EpiParams* ep) {
   ep->out_rows = a.out_rows;
   ep->bias = a.bias;
   ep->bias_bs = a.bias_bstride;
+  ep->live = a.live_units;
+  ep->live_mul = a.live_mul;
+  QVC_REQUIRE(!a.live_units || a.live_mul >= 1, "conv1d: live_units needs live_mul >= 1 (got %d)", a.live_mul);
   QVC_REQUIRE(a.epilogue >= QVC_EPI_LINEAR && a.epilogue <= QVC_EPI_SAMPLE, "conv1d: bad epilogue %d", a.epilogue);
   if (a.epilogue == QVC_EPI_LINEAR) {
     QVC_REQUIRE(a.nseg == 1 || a.nseg == 2, "conv1d: nseg must be 1 or 2 (got %d)", a.nseg);

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       const int gs = p.gsize[gi];
       const uint32_t buf = ait & 1u;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+      const int lim = live_rows(p.ep, b);
       if constexpr (EPI == QVC_EPI_LINEAR) {
         auto context = [&](int ci, LinCtx& k) -> bool {            // false: no live channel in this lane quarter
           const int nvalid = p.valid[gi][ci];
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           k.all_ok = __all_sync(0xffffffffu, k.ok);
           k.c = k.ok ? c : 0;
           k.b = b;
+          k.lim = lim;
           k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
           return true;
         };
@@ -265,8 +267,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             const int nv = min(32, p.ep.out_rows - t);
             if (nv <= 0) break;
             const uint32_t ta_lo = tbase + (uint32_t)(ci * N + col), ta_hi = tbase + (uint32_t)((ci + nlo) * N + col);
-            if constexpr (EPI == QVC_EPI_GATE) epi_gate_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, all_ok, bias_lo, bias_hi, ta_lo, ta_hi);
-            else                               epi_sample_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, bias_lo, bias_hi, ta_lo, ta_hi);
+            if constexpr (EPI == QVC_EPI_GATE) epi_gate_cols<OPF>(p.ep, b, t, nv, lim - t, ok ? n : 0, ok, all_ok, bias_lo, bias_hi, ta_lo, ta_hi);
+            else                               epi_sample_cols<OPF>(p.ep, b, t, nv, lim - t, ok ? n : 0, ok, bias_lo, bias_hi, ta_lo, ta_hi);
           }
         }
       }

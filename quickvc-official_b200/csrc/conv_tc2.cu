@@ -246,6 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           k.all_ok = __all_sync(0xffffffffu, k.ok);
           k.c = k.ok ? c : 0;
           k.b = b;
+          k.lim = live_rows(p.ep, b);
           k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
         }
         auto frames_at = [&](int col) -> int {
@@ -278,11 +279,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           const bool all_ok = __all_sync(0xffffffffu, ok);
           const float* bias = p.ep.bias + (int64_t)b * p.ep.bias_bs;
           const float bias_lo = ok ? bias[n] : 0.f, bias_hi = ok ? bias[p.ep.half + n] : 0.f;
+          const int lim = live_rows(p.ep, b);
           for (int col = col_begin; col < col_end; col += 32) {
             const int t = t0 + col;
             const int nv = min(32, p.ep.out_rows - t);
             if (nv <= 0) break;
-            epi_gate_cols<OPF>(p.ep, b, t, nv, ok ? n : 0, ok, all_ok, bias_lo, bias_hi, tbase + (uint32_t)col,
+            epi_gate_cols<OPF>(p.ep, b, t, nv, lim - t, ok ? n : 0, ok, all_ok, bias_lo, bias_hi, tbase + (uint32_t)col,
                                tbase + (uint32_t)(PN + col));
           }
         }

@@ -168,6 +168,7 @@ struct LinCtx {
   bool ok;                  // this lane owns a live channel
   bool all_ok;              // ... and so does every lane of the warp
   float bias;
+  int lim;                  // live rows of utterance b (ragged batches): operand rows >= lim are written as zero
 };
 
 // loads only: the residual if the segment has one (fp32, or the operand-format copy -- kept as raw bits here, decoded
@@ -263,6 +264,7 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = ab * (v[i] + k.bias);
     }
+    const int nlive = k.lim - th;                    // rows of this block inside the utterance's own length
     const bool full = k.all_ok && nvh >= 32;
     if (sg.raw.present()) {
       float* wp = sg.raw.at<float>(k.b, th, k.c);
@@ -279,13 +281,13 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
     if (sg.op.present()) {
       OT* op = sg.op.at<OT>(k.b, th, k.c);
       const int ld = sg.op.ld;
-      if (full) {
+      if (full && nlive >= 32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) op[i * ld] = to_operand<OPF>(fmaxf(v[i], v[i] * slope));   // leaky-relu, slope <= 1
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (k.ok && i < nvh) op[i * ld] = to_operand<OPF>(leaky(v[i], slope));
+          if (k.ok && i < nvh) op[i * ld] = to_operand<OPF>(i < nlive ? leaky(v[i], slope) : 0.f);
       }
     }
   }
@@ -302,7 +304,7 @@ __device__ __forceinline__ float fast_gate(float x, float y) {
 }
 
 template <int OPF>
-__device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t, int nv, int n, bool ok, bool all_ok,
+__device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t, int nv, int nlive, int n, bool ok, bool all_ok,
                                               float bias_lo, float bias_hi, uint32_t taddr_lo, uint32_t taddr_hi) {
   using OT = typename OpType<OPF>::type;
   float lo[32], hi[32];
@@ -323,19 +325,19 @@ __device__ __forceinline__ void epi_gate_cols(const EpiParams& ep, int b, int t,
   if (sg.op.present()) {
     OT* op = sg.op.at<OT>(b, t, n);
     const int ld = sg.op.ld;
-    if (full) {
+    if (full && nlive >= 32) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) op[i * ld] = to_operand<OPF>(lo[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (ok && i < nv) op[i * ld] = to_operand<OPF>(lo[i]);
+        if (ok && i < nv) op[i * ld] = to_operand<OPF>(i < nlive ? lo[i] : 0.f);
     }
   }
 }
 
 template <int OPF>
-__device__ __forceinline__ void epi_sample_cols(const EpiParams& ep, int b, int t, int nv, int n, bool ok,
+__device__ __forceinline__ void epi_sample_cols(const EpiParams& ep, int b, int t, int nv, int nlive, int n, bool ok,
                                                 float bias_lo, float bias_hi, uint32_t taddr_lo, uint32_t taddr_hi) {
   using OT = typename OpType<OPF>::type;
   float m[32], lg[32], nz[32];
@@ -381,7 +383,7 @@ __device__ __forceinline__ void epi_sample_cols(const EpiParams& ep, int b, int 
     const int64_t ld = sg.op.ld;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (ok && i < nv) op[i * ld] = to_operand<OPF>(nz[i]);
+      if (ok && i < nv) op[i * ld] = to_operand<OPF>(i < nlive ? nz[i] : 0.f);
   }
 }
 

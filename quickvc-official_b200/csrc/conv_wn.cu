@@ -348,6 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
         kx[a].all_ok = __all_sync(0xffffffffu, kx[a].ok);
         kx[a].c = kx[a].ok ? c : 0;
         kx[a].b = b;
+        kx[a].lim = live_rows(p.ep, b);
         kx[a].bias = (p.ep.bias && kx[a].ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
       }
       const int col = h * HN;

@@ -99,6 +99,8 @@ struct Ctx {
   const qvc_model* m;
   cudaStream_t st;
   size_t E;
+  int T;                         // unit frames the batch is padded to
+  const int32_t* lengths;        // device [batch] live unit frames per utterance, or nullptr (ragged batches)
 };
 
 inline qvc_tensor tens(const void* p, int64_t bs, int ld) { return qvc_tensor{const_cast<void*>(p), bs, ld, 0}; }
@@ -118,6 +120,9 @@ qvc_conv_args layer_args(const Ctx& c, int li, qvc_tensor x, int batch, int x_ro
   a.cout = L.cout; a.k = L.k; a.dil = L.dil; a.pad_left = L.pad_left;
   a.epilogue = QVC_EPI_LINEAR; a.nseg = 1;
   a.opformat = c.m->opformat; a.backend = c.m->backend;
+  // ragged batches: operand rows past an utterance's own length are written as zero, so that every later
+  // convolution sees the zero padding it would see at the end of that utterance alone
+  if (c.lengths && out_rows % c.T == 0) { a.live_units = c.lengths; a.live_mul = out_rows / c.T; }
   return a;
 }
 
@@ -228,12 +233,14 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
 }
 
 // Multistream_iSTFT_Generator.forward (models.py:360-408) on the whole batch, sub-batch by sub-batch.
-int run_decoder(const Ctx& c, const Buffers& bf, const Shapes& s, const void* zO, const float* condvec,
+int run_decoder(const Ctx& whole, const Buffers& bf, const Shapes& s, const void* zO, const float* condvec,
                 float* wave, const qvc_taps* taps) {
   const int T = s.T, R0 = UP0 * T, R1 = UP0 * UP1 * T, RP = R1 + 1;
-  const size_t E = c.E;
+  const size_t E = whole.E;
   for (int b0 = 0; b0 < s.B; b0 += s.cb) {
     const int cb = (s.B - b0 < s.cb) ? s.B - b0 : s.cb;
+    Ctx c = whole;
+    if (c.lengths) c.lengths += b0;
     const char* zO_b = reinterpret_cast<const char*>(zO) + (size_t)b0 * T * HID * E;
     // conv_pre + cond(g): the conditioning is a per-utterance bias (models.py:372)
     {
@@ -302,7 +309,7 @@ int run_decoder(const Ctx& c, const Buffers& bf, const Shapes& s, const void* zO
         QVC_PROPAGATE(from_series_major(bf.cpR, C_POST, (int64_t)RP * C_POST, taps->conv_post + (size_t)b0 * C_POST * RP,
                                         cb, C_POST, RP, false, c.st));
     }
-    QVC_PROPAGATE(qvc_tail(&c.m->tail, bf.cpR, C_POST, cb, RP, wave + (size_t)b0 * 16 * R1,
+    QVC_PROPAGATE(qvc_tail(&c.m->tail, bf.cpR, C_POST, cb, RP, c.lengths, UP0 * UP1, wave + (size_t)b0 * 16 * R1,
                            (taps && taps->y_mb) ? taps->y_mb + (size_t)b0 * 4 * 4 * R1 : nullptr,
                            (qvc_stream_t)c.st));
   }
@@ -363,7 +370,7 @@ extern "C" size_t qvc_infer_workspace_bytes(const qvc_model* m, int batch, int f
 }
 
 extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel, const float* noise,
-                         const float* g_in, int batch, int frames, int mel_batch, int mel_frames,
+                         const float* g_in, const int32_t* lengths, int batch, int frames, int mel_batch, int mel_frames,
                          float* wave, const qvc_taps* taps, void* workspace, size_t workspace_bytes,
                          qvc_stream_t stream) {
   QVC_PROPAGATE(check_model(m));
@@ -390,13 +397,13 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
     set_error("qvc_infer: workspace %zu < %zu", workspace_bytes, need + 256);
     return QVC_ERR_WORKSPACE;
   }
-  Ctx c{m, (cudaStream_t)stream, opformat_bytes(m->opformat)};
+  Ctx c{m, (cudaStream_t)stream, opformat_bytes(m->opformat), frames, lengths};
   const int B = batch, T = frames;
   const int64_t bs = (int64_t)T * HID;
 
   // inputs -> series-major
-  QVC_PROPAGATE(qvc_to_series_major(unit, bf.unitO, B, UNIT_CH, T, m->opformat, stream));
-  QVC_PROPAGATE(qvc_to_series_major(noise, bf.noiseT, B, HID, T, QVC_OPF_F32, stream));
+  QVC_PROPAGATE(to_series_major(unit, bf.unitO, B, UNIT_CH, T, m->opformat, lengths, c.st));
+  QVC_PROPAGATE(to_series_major(noise, bf.noiseT, B, HID, T, QVC_OPF_F32, lengths, c.st));
 
   // speaker embedding and the per-utterance bias vectors derived from it (models.py:635), on the
   // side stream when the encoder has to run
@@ -475,8 +482,8 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
   return run_decoder(c, bf, s, bf.zO, bf.condvec, wave, taps);
 }
 
-extern "C" int qvc_decode(const qvc_model* m, const float* z, const float* g, int g_batch, int batch,
-                          int frames, float* wave, const qvc_taps* taps, void* workspace,
+extern "C" int qvc_decode(const qvc_model* m, const float* z, const float* g, int g_batch,
+                          const int32_t* lengths, int batch, int frames, float* wave, const qvc_taps* taps, void* workspace,
                           size_t workspace_bytes, qvc_stream_t stream) {
   QVC_PROPAGATE(check_model(m));
   QVC_REQUIRE(z && g && wave && workspace, "qvc_decode: null pointer");
@@ -492,8 +499,8 @@ extern "C" int qvc_decode(const qvc_model* m, const float* z, const float* g, in
     set_error("qvc_decode: workspace %zu < %zu", workspace_bytes, need + 256);
     return QVC_ERR_WORKSPACE;
   }
-  Ctx c{m, (cudaStream_t)stream, opformat_bytes(m->opformat)};
-  QVC_PROPAGATE(qvc_to_series_major(z, bf.zO, batch, HID, frames, m->opformat, stream));
+  Ctx c{m, (cudaStream_t)stream, opformat_bytes(m->opformat), frames, lengths};
+  QVC_PROPAGATE(to_series_major(z, bf.zO, batch, HID, frames, m->opformat, lengths, c.st));
   QVC_PROPAGATE(cond_vectors(m->cond_w, m->cond_b, g, g_batch, m->cond_rows, bf.condvec, c.st));
   return run_decoder(c, bf, s, bf.zO, bf.condvec, wave, taps);
 }

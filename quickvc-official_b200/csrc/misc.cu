@@ -26,16 +26,17 @@ namespace {
 template <int OPF>
 __global__ void __launch_bounds__(256) to_series_kernel(const float* __restrict__ src,
                                                         typename OpType<OPF>::type* __restrict__ dst,
-                                                        int C, int T) {
+                                                        int C, int T, const int32_t* __restrict__ live) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float* s = src + (int64_t)b * C * T;
+  const int Tb = live ? min(T, live[b]) : T;          // ragged batches: padding frames become zero rows
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + 8 * i, t = t0 + tx;
-    tile[ty + 8 * i][tx] = (c < C && t < T) ? s[(int64_t)c * T + t] : 0.f;
+    tile[ty + 8 * i][tx] = (c < C && t < Tb) ? s[(int64_t)c * T + t] : 0.f;
   }
   __syncthreads();
   auto* d = dst + (int64_t)b * T * C;
@@ -123,20 +124,26 @@ int reflect_row(void* base, int64_t bstride_bytes, int row_bytes, int batch, cud
 
 using namespace qvc;
 
-extern "C" int qvc_to_series_major(const float* src, void* dst, int batch, int channels, int frames,
-                                   int opformat, qvc_stream_t stream) {
+namespace qvc {
+int to_series_major(const float* src, void* dst, int batch, int channels, int frames, int opformat,
+                    const int32_t* live, cudaStream_t st) {
   QVC_REQUIRE(src && dst, "qvc_to_series_major: null pointer");
   QVC_REQUIRE(batch >= 0 && batch <= 65535 && channels > 0 && frames >= 0, "qvc_to_series_major: bad shape");
   if (batch == 0 || frames == 0) return QVC_OK;
   dim3 grid((frames + 31) / 32, (channels + 31) / 32, batch);
-  cudaStream_t st = (cudaStream_t)stream;
   switch (opformat) {
-    case QVC_OPF_F32:  to_series_kernel<QVC_OPF_F32><<<grid, 256, 0, st>>>(src, (float*)dst, channels, frames); break;
-    case QVC_OPF_TF32: to_series_kernel<QVC_OPF_TF32><<<grid, 256, 0, st>>>(src, (float*)dst, channels, frames); break;
-    case QVC_OPF_BF16: to_series_kernel<QVC_OPF_BF16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, channels, frames); break;
+    case QVC_OPF_F32:  to_series_kernel<QVC_OPF_F32><<<grid, 256, 0, st>>>(src, (float*)dst, channels, frames, live); break;
+    case QVC_OPF_TF32: to_series_kernel<QVC_OPF_TF32><<<grid, 256, 0, st>>>(src, (float*)dst, channels, frames, live); break;
+    case QVC_OPF_BF16: to_series_kernel<QVC_OPF_BF16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, channels, frames, live); break;
     default: set_error("qvc_to_series_major: bad opformat %d", opformat); return QVC_ERR_ARG;
   }
   return post_launch("to_series_kernel");
+}
+}  // namespace qvc
+
+extern "C" int qvc_to_series_major(const float* src, void* dst, int batch, int channels, int frames,
+                                   int opformat, qvc_stream_t stream) {
+  return to_series_major(src, dst, batch, channels, frames, opformat, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int qvc_from_series_major(const float* src, int ld, float* dst, int batch, int channels,

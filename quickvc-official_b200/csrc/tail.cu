@@ -33,6 +33,8 @@ struct TailParams {
   const float* synth;   // [4][4][17]
   float* wave;
   float* y_mb;
+  const int32_t* live_units;   // ragged batches: utterance b has live_units[b] * frames_per_unit + 1 frames (nullptr: all)
+  int32_t frames_per_unit;
   // host copies, present when the caller supplied them: as kernel parameters they live in the constant bank,
   // so every coefficient is an FFMA operand instead of a shared-memory load
   float Ec[4 * 4 * 17];
@@ -57,7 +59,9 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ 
   const int q0 = blockIdx.x * TQ;                   // first sub-band sample of the tile
   const int fq = q0 >> 2;
   const int f_lo = fq - 3;                          // frame held in slot 0
-  const int F = p.frames;
+  const int FS = p.frames;                          // frames / sub-band samples the buffers are laid out for
+  const int nys = 4 * (FS - 1);
+  const int F = p.live_units ? min(FS, p.live_units[b] * p.frames_per_unit + 1) : FS;   // this utterance's own
   const int ny = 4 * (F - 1);                       // sub-band samples per band
 
   if (tid < 16) {
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ 
   if (!CONST_COEF)
     for (int i = tid; i < 4 * 4 * 17; i += NTHREADS) E[i] = p.synth[i];
 
-  const float* pb = p.post + (int64_t)b * F * p.ld;
+  const float* pb = p.post + (int64_t)b * FS * p.ld;
   __syncthreads();                                  // W / W2 / E visible
 
   // 2. one (frame, band) per thread: polar -> inverse real DFT -> window
@@ -151,22 +155,24 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ 
   // 4. polyphase synthesis: wave[4q + r] = sum_s sum_e E[s][r][e] * y[s][q + 8 - e]
   if (tid < TQ) {
     const int q = q0 + tid;
-    if (q < ny) {
+    if (q < nys) {
       float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (q < ny) {                                 // past the utterance's own end: zeros
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < 4; ++s) {
 #pragma unroll
-        for (int e = 0; e < 17; ++e) {
-          const float yv = Y[s][tid + 16 - e];
+          for (int e = 0; e < 17; ++e) {
+            const float yv = Y[s][tid + 16 - e];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) o[r] = fmaf(CONST_COEF ? p.Ec[(s * 4 + r) * 17 + e] : E[(s * 4 + r) * 17 + e], yv, o[r]);
+            for (int r = 0; r < 4; ++r) o[r] = fmaf(CONST_COEF ? p.Ec[(s * 4 + r) * 17 + e] : E[(s * 4 + r) * 17 + e], yv, o[r]);
+          }
         }
       }
-      *reinterpret_cast<float4*>(p.wave + (int64_t)b * 4 * ny + 4 * (int64_t)q) =
+      *reinterpret_cast<float4*>(p.wave + (int64_t)b * 4 * nys + 4 * (int64_t)q) =
           make_float4(o[0], o[1], o[2], o[3]);
       if (p.y_mb) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) p.y_mb[((int64_t)b * 4 + s) * ny + q] = Y[s][tid + 8];
+        for (int s = 0; s < 4; ++s) p.y_mb[((int64_t)b * 4 + s) * nys + q] = Y[s][tid + 8];
       }
     }
   }
@@ -177,11 +183,12 @@ __global__ void __launch_bounds__(NTHREADS) tail_kernel(const __grid_constant__ 
 }  // namespace qvc
 
 extern "C" int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, int batch, int frames,
-                        float* wave, float* y_mb, qvc_stream_t stream) {
+                        const int32_t* live_units, int frames_per_unit, float* wave, float* y_mb, qvc_stream_t stream) {
   using namespace qvc;
   QVC_REQUIRE(w && w->window && w->synth && post && wave, "qvc_tail: null pointer");
   QVC_REQUIRE(ld >= NCH && ld % 4 == 0 && ((uintptr_t)post & 15) == 0, "qvc_tail: post must be 16-byte aligned with ld %% 4 == 0");
   QVC_REQUIRE(batch >= 0 && frames >= 1, "qvc_tail: bad shape");
+  QVC_REQUIRE(!live_units || frames_per_unit >= 1, "qvc_tail: live_units needs frames_per_unit >= 1");
   const int ny = 4 * (frames - 1);
   if (batch == 0 || ny == 0) return QVC_OK;
   QVC_REQUIRE(batch <= 65535, "qvc_tail: batch too large for one launch");
@@ -189,6 +196,7 @@ extern "C" int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, in
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   p.post = post; p.ld = ld; p.frames = frames; p.window = w->window; p.synth = w->synth; p.wave = wave; p.y_mb = y_mb;
+  p.live_units = live_units; p.frames_per_unit = frames_per_unit;
   dim3 grid((ny + TQ - 1) / TQ, batch);
   if (w->synth_host && w->window_host) {
     memcpy(p.Ec, w->synth_host, sizeof(p.Ec));

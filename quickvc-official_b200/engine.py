@@ -34,7 +34,7 @@ class InferEngine:
         self._folded: Optional[fold.Folded] = None
         self._model: Optional[capi.Model] = None
         self._device: Optional[torch.device] = None
-        self._ws: Dict[torch.device, Tensor] = {}
+        self._ws: Dict[Tuple[torch.device, int], Tensor] = {}     # one workspace per (device, stream)
         self.chunk_utts = int(chunk_utts)
         self.configure(precision, backend)
 
@@ -76,11 +76,15 @@ class InferEngine:
         return self._model
 
     def _workspace(self, device: torch.device, nbytes: int) -> Tensor:
-        ws = self._ws.get(device)
-        if ws is None or ws.numel() < nbytes:
-            self._ws.pop(device, None)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            self._ws[device] = ws
+        # keyed by the current stream: calls enqueued on different streams run concurrently and must not share
+        # scratch memory (include/qvc_b200.h: re-entrant across streams when each stream has its own workspace)
+        with torch.cuda.device(device):
+            key = (device, torch.cuda.current_stream(device).cuda_stream)
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < nbytes:
+                self._ws.pop(key, None)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                self._ws[key] = ws
         return ws
 
     # ------------------------------------------------------------------ helpers
@@ -95,6 +99,18 @@ class InferEngine:
     @staticmethod
     def _stream(device: torch.device) -> int:
         return torch.cuda.current_stream(device).cuda_stream
+
+    @staticmethod
+    def _lengths(lengths: Optional[Tensor], B: int, T: int, device: torch.device) -> Optional[Tensor]:
+        """(B,) live frames per utterance as a device int32 tensor; range-checked on the host when it is a host
+        tensor (a device tensor is trusted: reading it back would synchronise the stream)."""
+        if lengths is None:
+            return None
+        if lengths.dim() != 1 or lengths.shape[0] != B or lengths.dtype.is_floating_point:
+            raise ValueError(f"lengths must be an integer tensor of shape ({B},), got {lengths.dtype} {tuple(lengths.shape)}")
+        if lengths.device.type == "cpu" and B and (int(lengths.min()) < 1 or int(lengths.max()) > T):
+            raise ValueError(f"lengths must lie in [1, {T}], got [{int(lengths.min())}, {int(lengths.max())}]")
+        return lengths.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
 
     def _make_taps(self, taps: Optional[Dict[str, Tensor]], names, B: int, T: int, n_embed: int,
                    device: torch.device) -> Tuple[Optional[capi.Taps], Dict[str, Tensor]]:
@@ -117,7 +133,8 @@ class InferEngine:
 
     # ------------------------------------------------------------------ entry points
     def infer(self, unit: Tensor, mel: Optional[Tensor], noise: Optional[Tensor] = None,
-              taps: Optional[Dict[str, Tensor]] = None, g: Optional[Tensor] = None) -> Tensor:
+              taps: Optional[Dict[str, Tensor]] = None, g: Optional[Tensor] = None,
+              lengths: Optional[Tensor] = None) -> Tensor:
         if unit.dim() != 3 or unit.shape[1] != 256:
             raise ValueError(f"unit must be (B, 256, T), got {tuple(unit.shape)}")
         device = unit.device
@@ -127,6 +144,7 @@ class InferEngine:
         if B == 0 or T == 0:
             return torch.empty(B, 1, 320 * T, device=device)
         unit = self._f32c(unit, "unit", device)
+        lens = self._lengths(lengths, B, T, device)
         if noise is None:
             noise = torch.randn((B, 192, T), device=device, dtype=torch.float32)     # models.py:94
         else:
@@ -157,8 +175,8 @@ class InferEngine:
         need = lib.qvc_infer_workspace_bytes(C.byref(model), B, T, mel_b, mel_t)
         ws = self._workspace(device, need)
         with torch.cuda.device(device):
-            status = lib.qvc_infer(C.byref(model), unit.data_ptr(), mel_ptr, noise.data_ptr(), g_ptr, B, T, mel_b,
-                                   mel_t, wave.data_ptr(), C.byref(tap_struct) if tap_struct is not None else None,
+            status = lib.qvc_infer(C.byref(model), unit.data_ptr(), mel_ptr, noise.data_ptr(), g_ptr,
+                                   lens.data_ptr() if lens is not None else None, B, T, mel_b, mel_t, wave.data_ptr(), C.byref(tap_struct) if tap_struct is not None else None,
                                    ws.data_ptr(), ws.numel(), self._stream(device))
         capi.check(status, "qvc_infer")
         if taps is not None:
@@ -188,7 +206,8 @@ class InferEngine:
         capi.check(status, "qvc_spk_embed")
         return g
 
-    def decode(self, z: Tensor, g: Tensor, taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    def decode(self, z: Tensor, g: Tensor, taps: Optional[Dict[str, Tensor]] = None,
+               lengths: Optional[Tensor] = None) -> Tensor:
         if z.dim() != 3 or z.shape[1] != 192:
             raise ValueError(f"z must be (B, 192, T), got {tuple(z.shape)}")
         device = z.device
@@ -196,6 +215,7 @@ class InferEngine:
         lib = capi.load()
         B, _, T = z.shape
         z = self._f32c(z, "z", device)
+        lens = self._lengths(lengths, B, T, device)
         g = self._f32c(g.reshape(g.shape[0], -1), "g", device)
         if g.shape[1] != 256 or g.shape[0] not in (1, B):
             raise ValueError(f"g must be (1|B, 256[, 1]), got {tuple(g.shape)}")
@@ -204,7 +224,8 @@ class InferEngine:
         need = lib.qvc_infer_workspace_bytes(C.byref(model), B, T, 0, 0)
         ws = self._workspace(device, need)
         with torch.cuda.device(device):
-            status = lib.qvc_decode(C.byref(model), z.data_ptr(), g.data_ptr(), g.shape[0], B, T, wave.data_ptr(),
+            status = lib.qvc_decode(C.byref(model), z.data_ptr(), g.data_ptr(), g.shape[0],
+                                    lens.data_ptr() if lens is not None else None, B, T, wave.data_ptr(),
                                     C.byref(tap_struct) if tap_struct is not None else None, ws.data_ptr(),
                                     ws.numel(), self._stream(device))
         capi.check(status, "qvc_decode")

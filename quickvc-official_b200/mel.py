@@ -19,7 +19,7 @@ from torch import Tensor
 from . import capi
 
 _cache: Dict[Tuple, Tuple[capi.MelWeights, Tensor, Tensor]] = {}
-_ws: Dict[torch.device, Tensor] = {}
+_ws: Dict[Tuple[torch.device, int], Tensor] = {}     # one workspace per (device, stream)
 
 
 def slaney_mel_filterbank(sr: int, n_fft: int, n_mels: int, fmin: float = 0.0, fmax: Optional[float] = None) -> Tensor:
@@ -99,11 +99,12 @@ def wave_to_mel(y: Tensor, n_fft: int, num_mels: int, sampling_rate: int, hop_si
     frames = lib.qvc_mel_frames(C.byref(w), T)
     mel = torch.empty(B, num_mels, frames, device=device, dtype=torch.float32)
     need = lib.qvc_mel_workspace_bytes(C.byref(w), B, T)
-    ws = _ws.get(device)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
-        _ws[device] = ws
     with torch.cuda.device(device):
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        ws = _ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            _ws[key] = ws
         st = lib.qvc_wave_to_mel(C.byref(w), y.data_ptr(), B, T, mel.data_ptr(), ws.data_ptr(), ws.numel(),
                                  torch.cuda.current_stream(device).cuda_stream)
     capi.check(st, "qvc_wave_to_mel")

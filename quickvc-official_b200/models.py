@@ -293,14 +293,17 @@ class SynthesizerTrn(nn.Module):
 
     @torch.no_grad()
     def infer(self, unit: Tensor, mel: Tensor, *, noise: Optional[Tensor] = None,
-              taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+              taps: Optional[Dict[str, Tensor]] = None, lengths: Optional[Tensor] = None) -> Tensor:
         """unit (B,256,T) fp32, mel (1,80,Tm) fp32 [or (B,80,Tm<=128)] -> waveform (B,1,320 T) fp32.
 
         `noise` (B,192,T) replaces the `torch.randn_like` draw of models.py:94 (default: drawn here
         with torch's generator, so seeded runs are reproducible).  `taps`, if a dict, is filled with
         the per-stage tensors of SURVEY.md section 8a in the reference layout.
+        `lengths` (B,) integer frames per utterance, 1 <= lengths[b] <= T, declares a ragged batch padded to T:
+        wave[b, 0, :320*lengths[b]] is then exactly what `infer(unit[b:b+1, :, :lengths[b]], ...)` returns for
+        that utterance alone (the reference converts one utterance per call, convert.py:59-86), the rest zeros.
         """
-        return self._engine.infer(unit, mel, noise=noise, taps=taps)
+        return self._engine.infer(unit, mel, noise=noise, taps=taps, lengths=lengths)
 
     @torch.no_grad()
     def embed_speaker(self, mel: Tensor) -> Tensor:
@@ -309,10 +312,13 @@ class SynthesizerTrn(nn.Module):
         return self._engine.embed(mel)
 
     @torch.no_grad()
-    def infer_with_embedding(self, unit: Tensor, g: Tensor, *, noise: Optional[Tensor] = None) -> Tensor:
-        return self._engine.infer(unit, None, noise=noise, g=g)
+    def infer_with_embedding(self, unit: Tensor, g: Tensor, *, noise: Optional[Tensor] = None,
+                             lengths: Optional[Tensor] = None) -> Tensor:
+        """`infer` with the speaker embedding(s) `g` (1|B, 256) of `embed_speaker` instead of a mel."""
+        return self._engine.infer(unit, None, noise=noise, g=g, lengths=lengths)
 
     @torch.no_grad()
-    def decode(self, z: Tensor, g: Tensor, *, taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
-        """dec(z, g=g)[0] (models.py:640): z (B,192,T), g (1|B,256,1) -> (B,1,320 T)."""
-        return self._engine.decode(z, g, taps=taps)
+    def decode(self, z: Tensor, g: Tensor, *, taps: Optional[Dict[str, Tensor]] = None,
+               lengths: Optional[Tensor] = None) -> Tensor:
+        """dec(z, g=g)[0] (models.py:640): z (B,192,T), g (1|B,256,1) -> (B,1,320 T); `lengths` as for `infer`."""
+        return self._engine.decode(z, g, taps=taps, lengths=lengths)

@@ -21,6 +21,8 @@ opf = capi.OPF_TF32 if prec == "tf32" else capi.OPF_BF16
 E = 4 if prec == "tf32" else 2
 DEV = "cuda:0"
 B = int(os.environ.get("CB_BATCH", "64"))
+ROWS_DIV = int(os.environ.get("CB_ROWS_DIV", "1"))      # 2: the 5 s clip geometry
+GRAPH = bool(int(os.environ.get("CB_GRAPH", "0")))      # time 20 launches replayed from a CUDA graph (no host gaps)
 
 # name, rows, cin, cout, k, dil, kind
 LAYERS = [
@@ -58,6 +60,7 @@ KEYS = ("QVC_TC_XPROM", "QVC_TC_DEBUG", "QVC_TC_SS", "QVC_TC_WS", "QVC_TC_G", "Q
 
 
 def run_layer(name, rows, cin, cout, k, dil, kind):
+    rows = rows // ROWS_DIV
     g = torch.Generator().manual_seed(1)
     x = to_op(torch.randn(B, rows, cin, generator=g), opf).to(DEV)
     w = to_op(torch.randn(cout, k, cin, generator=g) / (cin * k) ** 0.5, opf).to(DEV)
@@ -104,12 +107,28 @@ def run_layer(name, rows, cin, cout, k, dil, kind):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
-            n = 10
+            n = 20 if GRAPH else 10
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(n):
-                fn()
-            e.record()
+            if GRAPH:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn()
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for _ in range(n):
+                        fn()
+                graph.replay()
+                torch.cuda.synchronize()
+                s.record()
+                graph.replay()
+                e.record()
+            else:
+                s.record()
+                for _ in range(n):
+                    fn()
+                e.record()
             torch.cuda.synchronize()
             us = s.elapsed_time(e) * 1e3 / n
             print(f"{name:12s} {prec} {str(cfg):60s} {us:9.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {nbytes / us / 1e3:7.1f} GB/s", flush=True)

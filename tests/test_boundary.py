@@ -71,7 +71,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(capi.Tensor) == 24
     assert ctypes.sizeof(capi.EpiSegment) == 24 + 5 * 24 + 8
     assert ctypes.sizeof(capi.Layer) == 40
-    assert ctypes.sizeof(capi.ConvArgs) == 24 + 16 + 24 + 16 + 8 + 2 * 152 + 3 * 24 + 8
+    assert ctypes.sizeof(capi.ConvArgs) == 24 + 16 + 24 + 16 + 8 + 2 * 152 + 3 * 24 + 8 + 16
     assert ctypes.sizeof(capi.Model) == 16 + 114 * 40 + 24 + 11 * 8 + 4 * 8
 
 

@@ -230,7 +230,7 @@ def test_tail_matches_oracle(frames, batch, sd):
     post_sm = post.transpose(1, 2).contiguous().to(DEV)
     wave = torch.full((batch, 1, 16 * (frames - 1)), float("nan"), device=DEV)
     ymb = torch.full((batch, 4, 4 * (frames - 1)), float("nan"), device=DEV)
-    capi.check(lib.qvc_tail(C.byref(tw), post_sm.data_ptr(), 72, batch, frames, wave.data_ptr(), ymb.data_ptr(),
+    capi.check(lib.qvc_tail(C.byref(tw), post_sm.data_ptr(), 72, batch, frames, None, 0, wave.data_ptr(), ymb.data_ptr(),
                             stream()), "qvc_tail")
     torch.cuda.synchronize()
     # oracle: the decoder code after subband_conv_post (models.py:390-406)
@@ -247,7 +247,7 @@ def test_tail_matches_oracle(frames, batch, sd):
     tw2 = capi.TailWeights(win.data_ptr(), syn.data_ptr(), f.tensors["tail.window_host"].data_ptr(),
                            f.tensors["tail.synth_host"].data_ptr())
     wave2 = torch.full_like(wave, float("nan"))
-    capi.check(lib.qvc_tail(C.byref(tw2), post_sm.data_ptr(), 72, batch, frames, wave2.data_ptr(), None, stream()), "qvc_tail")
+    capi.check(lib.qvc_tail(C.byref(tw2), post_sm.data_ptr(), 72, batch, frames, None, 0, wave2.data_ptr(), None, stream()), "qvc_tail")
     torch.cuda.synchronize()
     assert torch.equal(wave2, wave)
 
