@@ -398,6 +398,19 @@ def run_ours(args, rank, local_rank, world):
             line[name] = latency(lambda: net.infer(u1, m5, noise=n1))
             line[name]["cached_speaker"] = latency(lambda: net.infer_with_embedding(u1, emb, noise=n1))
 
+        # SURVEY.md section 8f "next" #3: ragged batches -- the same B utterances with lengths drawn from 5 .. 10 s, sorted
+        # as the conversion driver does, padded to the longest; the rate counts live audio only
+        lens = torch.sort(torch.randint(T // 2, T + 1, (B,), generator=torch.Generator().manual_seed(3))).values
+        lens[-1] = T
+        lens_dev = lens.to(dev, torch.int32)
+        ms_rag, _ = timed(lambda: net.infer(unit, mel, noise=noise, lengths=lens_dev), max(3, args.steps // 2), 3)
+        live_s = float(lens.sum()) / 50.0
+        line["ragged_batch"] = {"value": live_s / (ms_rag * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_rag,
+                                "live_audio_s": live_s, "padded_audio_s": B * T / 50.0,
+                                "note": f"infer(unit, mel, lengths=...) on {B} utterances of 5..10 s padded to 10 s: each gets "
+                                        "exactly the samples of its own single-utterance call (tests/test_gpu_ragged.py); "
+                                        "padding frames are computed and masked, so the step time equals the dense batch's"}
+
         # SURVEY.md section 8f "next" #1: the target-mel front end (wave_to_mel, convert.py:75-77) for one 10 s target
         from quickvc_official_b200 import mel as qmel
         from oracle import mel_oracle

@@ -15,12 +15,13 @@ reference takes from libraries that are not dependencies here restated below:
                      or reads precomputed units from `--units-dir/<source stem>.{pt,npy}`.
 
 What is B200-specific: the reference converts one utterance at a time and leaves the GPU idle while the host reads,
-trims and writes files.  Here every utterance keeps the reference's exact single-utterance arithmetic (no padding of
-ragged lengths, which would change the samples near the end), and throughput comes from (1) one speaker embedding per
-distinct target file, (2) utterances with the same target and the same number of frames going through `infer` as one
-batch, (3) `streams` CUDA streams in round-robin, each with its own workspace, so that the short kernels of several
-single clips overlap on the 148 SMs, and (4) pinned device->host copies that overlap the next clips' kernels, with the
-WAV files written once their copy event has fired.
+trims and writes files.  Here every utterance still gets exactly the samples of its own single-utterance call, and
+throughput comes from (1) one speaker embedding per distinct target file, (2) ragged batches: utterances sorted by
+length go through `infer(..., lengths=...)` up to `max_batch` at a time -- the kernels write zeros past each
+utterance's own end, which is the zero padding that utterance's convolutions see alone (include/qvc_b200.h,
+qvc_infer `lengths`) -- (3) `streams` CUDA streams in round-robin, each with its own workspace, so that small batches
+and single clips overlap on the 148 SMs, and (4) pinned device->host copies that overlap the next batch's kernels, with
+the WAV files written once their copy event has fired.  `ragged=False` restricts batches to equal lengths and targets.
 """
 from __future__ import annotations
 
@@ -191,9 +192,19 @@ def load_hubert_soft(device: torch.device) -> ContentEncoder:
 
 # ---------------------------------------------------------------------------------------------- the driver
 @dataclass
+class _Item:
+    title: str
+    tgt: str
+    unit: Tensor                      # (1, 256, frames) on the device
+    noise: Optional[Tensor]           # (1, 192, frames) or None
+    frames: int
+
+
+@dataclass
 class _Pending:
     titles: List[str]
-    host: Tensor                      # pinned (B, 1, S)
+    frames: List[int]
+    host: Tensor                      # pinned (B, 1, 320 * max frames)
     done: torch.cuda.Event
 
 
@@ -201,7 +212,8 @@ class Converter:
     """`convert.py`'s synthesis loop.  `net` is a `quickvc_official_b200.SynthesizerTrn` on a CUDA device."""
 
     def __init__(self, net, hps: HParams, *, content_encoder: Optional[ContentEncoder] = None,
-                 units_dir: Optional[str] = None, streams: int = 4, max_batch: int = 64) -> None:
+                 units_dir: Optional[str] = None, streams: int = 2, max_batch: int = 64, ragged: bool = True,
+                 max_padding: float = 0.1) -> None:
         self.net = net
         self.hps = hps
         self.device = next(net.parameters()).device
@@ -212,9 +224,11 @@ class Converter:
         self.content_encoder = content_encoder
         self.units = UnitsDirectory(units_dir) if units_dir is not None else None
         self.max_batch = max(1, int(max_batch))
+        self.ragged = bool(ragged)
+        self.max_padding = float(max_padding)
         self._streams = [torch.cuda.Stream(self.device) for _ in range(max(1, int(streams)))]
         self._embeddings: Dict[str, Tensor] = {}
-        self.stats = {"utterances": 0, "calls": 0, "audio_seconds": 0.0, "targets": 0}
+        self.stats = {"utterances": 0, "calls": 0, "audio_seconds": 0.0, "padded_audio_seconds": 0.0, "targets": 0}
 
     # -- preprocessing, per file -------------------------------------------------------------------
     def speaker_embedding(self, tgt: str) -> Tensor:
@@ -233,9 +247,15 @@ class Converter:
             self.stats["targets"] += 1
         return g
 
-    def source_units(self, src: str) -> Tensor:
-        """(1, 256, T) on the device (convert.py:65-66,79)."""
-        if self.units is not None:
+    def source_units(self, src) -> Tensor:
+        """(1, 256, T) on the device (convert.py:65-66,79).  `src` is a file path, or the soft units themselves as a
+        (T, 256) / (1, T, 256) tensor (an in-memory caller that already ran its content encoder)."""
+        if isinstance(src, Tensor):
+            u = src.to(self.device, torch.float32, non_blocking=True)
+            u = u.unsqueeze(0) if u.dim() == 2 else u
+            if u.dim() != 3 or u.shape[0] != 1 or u.shape[2] != 256:
+                raise ValueError(f"units must be (T, 256) or (1, T, 256), got {tuple(src.shape)}")
+        elif self.units is not None:
             u = self.units.for_source(src, self.device)
         else:
             wav = load_wave(src, self.hps.data.sampling_rate)
@@ -243,54 +263,91 @@ class Converter:
         return u.transpose(2, 1).contiguous()
 
     # -- conversion ----------------------------------------------------------------------------------
+    def _plan(self, loaded: List["_Item"]) -> List[List["_Item"]]:
+        """Batches of utterances that go through one `infer` call.
+
+        ragged (default): utterances sorted by length and cut into batches of at most `max_batch`, closed early when
+        padding everything to the longest member would waste more than `max_padding` of the batch's frames; each batch
+        is one call with `lengths` (per-utterance speaker embeddings, so targets mix freely).
+        Otherwise: only utterances with the same target and the same number of frames share a call.
+        """
+        if not self.ragged:
+            groups: Dict[Tuple[str, int], List[_Item]] = {}
+            for it in loaded:
+                groups.setdefault((it.tgt, it.frames), []).append(it)
+            return [m[i:i + self.max_batch] for m in groups.values() for i in range(0, len(m), self.max_batch)]
+        batches: List[List[_Item]] = []
+        cur: List[_Item] = []
+        total = 0
+        for it in sorted(loaded, key=lambda x: x.frames):
+            if cur and (len(cur) >= self.max_batch or
+                        1.0 - (total + it.frames) / float(it.frames * (len(cur) + 1)) > self.max_padding):
+                batches.append(cur)
+                cur, total = [], 0
+            cur.append(it)
+            total += it.frames
+        if cur:
+            batches.append(cur)
+        return batches
+
     @torch.no_grad()
     def convert(self, items: Sequence[Tuple[str, str, str]], *, noise_seed: Optional[int] = None
                 ) -> Iterable[Tuple[str, np.ndarray]]:
-        """Yields `(title, waveform float32 (S,))` for every item, grouped by (target, frames); order within the list
-        is not preserved across groups.  `noise_seed` makes the prior's draw (models.py:94) reproducible: item i of the
-        list uses a generator seeded with `noise_seed + i`."""
+        """Yields `(title, waveform float32 (320 * frames,))` for every item; the order follows the batches, not the
+        list.  `noise_seed` makes the prior's draw (models.py:94) reproducible: item i of the list uses a generator
+        seeded with `noise_seed + i`, whatever batch it lands in."""
         sr = self.hps.data.sampling_rate
         main = torch.cuda.current_stream(self.device)
         # 1. speaker embeddings and units on the caller's stream (file reading dominates)
-        groups: Dict[Tuple[str, int], List[Tuple[str, Tensor, Optional[Tensor]]]] = {}
+        loaded: List[_Item] = []
         for index, (title, src, tgt) in enumerate(items):
             self.speaker_embedding(tgt)
             u = self.source_units(src)
             noise = None
-            if noise_seed is not None:               # item `index` always gets the same draw, whatever the grouping
+            if noise_seed is not None:
                 gen = torch.Generator(device=self.device)
                 gen.manual_seed(int(noise_seed) + index)
                 noise = torch.randn((1, 192, u.shape[2]), device=self.device, generator=gen)
-            groups.setdefault((tgt, u.shape[2]), []).append((title, u, noise))
+            loaded.append(_Item(title, tgt, u, noise, u.shape[2]))
         ready = torch.cuda.Event()
         ready.record(main)
-        # 2. one infer per group slice, streams in round-robin
+        # 2. one infer per batch, streams in round-robin
         pending: List[_Pending] = []
-        n_call = 0
-        for (tgt, frames), members in groups.items():
-            g = self._embeddings[tgt]
-            for i in range(0, len(members), self.max_batch):
-                part = members[i:i + self.max_batch]
-                s = self._streams[n_call % len(self._streams)]
-                n_call += 1
-                with torch.cuda.stream(s):
-                    s.wait_event(ready)
-                    unit = part[0][1] if len(part) == 1 else torch.cat([m[1] for m in part], dim=0)
-                    noise = None
-                    if part[0][2] is not None:
-                        noise = part[0][2] if len(part) == 1 else torch.cat([m[2] for m in part], dim=0)
-                    wave = self.net.infer_with_embedding(unit, g, noise=noise)
-                    host = torch.empty(wave.shape, dtype=torch.float32, pin_memory=True)
-                    host.copy_(wave, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(s)
-                pending.append(_Pending([m[0] for m in part], host, ev))
-                self.stats["calls"] += 1
-                self.stats["utterances"] += len(part)
-                self.stats["audio_seconds"] += len(part) * wave.shape[2] / sr
-                # hand finished clips back while later ones are still running
-                while pending and pending[0].done.query():
-                    yield from self._emit(pending.pop(0))
+        for n_call, part in enumerate(self._plan(loaded)):
+            s = self._streams[n_call % len(self._streams)]
+            frames = [it.frames for it in part]
+            t_max = max(frames)
+            with torch.cuda.stream(s):
+                s.wait_event(ready)
+                same_len = min(frames) == t_max
+                same_tgt = all(it.tgt == part[0].tgt for it in part)
+                if len(part) == 1:
+                    unit, noise = part[0].unit, part[0].noise
+                elif same_len:
+                    unit = torch.cat([it.unit for it in part], dim=0)
+                    noise = torch.cat([it.noise for it in part], dim=0) if part[0].noise is not None else None
+                else:
+                    unit = torch.zeros((len(part), 256, t_max), device=self.device)
+                    noise = torch.zeros((len(part), 192, t_max), device=self.device) if part[0].noise is not None else None
+                    for b, it in enumerate(part):
+                        unit[b, :, :it.frames] = it.unit[0]
+                        if noise is not None:
+                            noise[b, :, :it.frames] = it.noise[0]
+                g = self._embeddings[part[0].tgt] if same_tgt else torch.cat([self._embeddings[it.tgt] for it in part], dim=0)
+                lengths = None if same_len else torch.tensor(frames, dtype=torch.int32)
+                wave = self.net.infer_with_embedding(unit, g, noise=noise, lengths=lengths)
+                host = torch.empty(wave.shape, dtype=torch.float32, pin_memory=True)
+                host.copy_(wave, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s)
+            pending.append(_Pending([it.title for it in part], frames, host, ev))
+            self.stats["calls"] += 1
+            self.stats["utterances"] += len(part)
+            self.stats["audio_seconds"] += sum(frames) * 320 / sr
+            self.stats["padded_audio_seconds"] += len(part) * t_max * 320 / sr
+            # hand finished clips back while later ones are still running
+            while pending and pending[0].done.query():
+                yield from self._emit(pending.pop(0))
         for p in pending:
             p.done.synchronize()
             yield from self._emit(p)
@@ -298,10 +355,10 @@ class Converter:
             main.wait_stream(s)
 
     @staticmethod
-    def _emit(p: _Pending) -> Iterable[Tuple[str, np.ndarray]]:
+    def _emit(p: "_Pending") -> Iterable[Tuple[str, np.ndarray]]:
         arr = p.host.numpy()
         for b, title in enumerate(p.titles):
-            yield title, arr[b, 0]
+            yield title, arr[b, 0, :320 * p.frames[b]]
 
     def convert_list(self, txtpath: str, outdir: str, *, use_timestamp: bool = False,
                      noise_seed: Optional[int] = None) -> List[str]:
@@ -337,7 +394,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     parser.add_argument("--use_timestamp", default=False, action="store_true")
     parser.add_argument("--units-dir", type=str, default=None, help="precomputed soft units (<source stem>.pt/.npy) instead of torch.hub hubert_soft")
     parser.add_argument("--precision", type=str, default="tf32", choices=("tf32", "bf16", "fp32"))
-    parser.add_argument("--streams", type=int, default=4, help="CUDA streams the single-clip calls rotate over")
+    parser.add_argument("--streams", type=int, default=2, help="CUDA streams the infer calls rotate over")
+    parser.add_argument("--max-batch", type=int, default=64, help="utterances per infer call")
+    parser.add_argument("--no-ragged", action="store_true", help="only batch utterances of equal length and target")
     parser.add_argument("--seed", type=int, default=None, help="seed of the prior's noise draw (default: unseeded, as the reference)")
     args = parser.parse_args(argv)
 
@@ -347,7 +406,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     net = build_net(hps, args.ptfile, device, args.precision)
     print("Number of parameter: %.2fM" % (sum(p.nelement() for p in net.parameters()) / 1e6))
     encoder = None if args.units_dir else load_hubert_soft(device)
-    conv = Converter(net, hps, content_encoder=encoder, units_dir=args.units_dir, streams=args.streams)
+    conv = Converter(net, hps, content_encoder=encoder, units_dir=args.units_dir, streams=args.streams,
+                     max_batch=args.max_batch, ragged=not args.no_ragged)
     print("Synthesizing...")
     t0 = time.perf_counter()
     written = conv.convert_list(args.txtpath, args.outdir, use_timestamp=args.use_timestamp, noise_seed=args.seed)

@@ -36,8 +36,8 @@ with tempfile.TemporaryDirectory() as d:
         lines.append(f"c{i}|s{i}.wav|{d}/tgt{i % 4}.wav")
     open(f"{d}/list.txt", "w").write("\n".join(lines) + "\n")
     items = cv.read_list(f"{d}/list.txt")
-    for streams in (1, 2, 4, 8):
-        conv = cv.Converter(net, hps, units_dir=f"{d}/units", streams=streams)
+    for streams, ragged in ((1, False), (4, False), (1, True), (2, True)):
+        conv = cv.Converter(net, hps, units_dir=f"{d}/units", streams=streams, ragged=ragged)
         for _ in conv.convert(items[:16]):
             pass
         torch.cuda.synchronize()
@@ -48,5 +48,13 @@ with tempfile.TemporaryDirectory() as d:
         t1 = time.perf_counter()
         conv.convert_list(f"{d}/list.txt", f"{d}/out{streams}")
         dt_files = time.perf_counter() - t1
-        print(f"{prec} streams={streams}: {n} clips, {total / 50:.0f} audio-s in {dt * 1e3:.0f} ms = {total / 50 / dt:.0f} audio-s/s "
-              f"({dt / n * 1e3:.2f} ms per clip); with WAV writing {total / 50 / dt_files:.0f} audio-s/s", flush=True)
+        # units already on the device (what a content encoder running on the GPU hands over): no file reads
+        mem_items = [(t, conv.source_units(s).transpose(2, 1).contiguous(), g) for t, s, g in items]
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        n2 = sum(1 for _ in conv.convert(mem_items))
+        torch.cuda.synchronize()
+        dt_mem = time.perf_counter() - t2
+        print(f"{prec} ragged={ragged} streams={streams} calls={conv.stats['calls']} padding={conv.stats['padded_audio_seconds'] / conv.stats['audio_seconds'] - 1:.1%}: {n} clips, {total / 50:.0f} audio-s in {dt * 1e3:.0f} ms = {total / 50 / dt:.0f} audio-s/s "
+              f"({dt / n * 1e3:.2f} ms per clip); with WAV writing {total / 50 / dt_files:.0f} audio-s/s; "
+              f"units resident on the device {total / 50 / dt_mem:.0f} audio-s/s ({dt_mem * 1e3:.0f} ms)", flush=True)

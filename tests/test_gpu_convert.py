@@ -46,20 +46,25 @@ def workdir(tmp_path_factory):
     return d
 
 
-@pytest.mark.parametrize("streams", [1, 3])
-def test_convert_list_matches_single_clip_chain(workdir, sd, model_cfg, streams):
+@pytest.mark.parametrize("streams,ragged", [(1, False), (3, False), (2, True)])
+def test_convert_list_matches_single_clip_chain(workdir, sd, model_cfg, streams, ragged):
     hps = cv.HParams(data=DATA, train={"segment_size": 10240}, model=model_cfg)
     net = cv.build_net(hps, None, torch.device(DEV))
     net.load_state_dict(sd)
-    conv = cv.Converter(net, hps, units_dir=str(workdir / "units"), streams=streams, max_batch=2)
-    out = workdir / f"out{streams}"
+    conv = cv.Converter(net, hps, units_dir=str(workdir / "units"), streams=streams, max_batch=2 if not ragged else 4,
+                        ragged=ragged, max_padding=0.5)
+    out = workdir / f"out{streams}{ragged}"
     written = conv.convert_list(str(workdir / "convert.txt"), str(out), noise_seed=100)
     items = cv.read_list(str(workdir / "convert.txt"))
     assert sorted(os.path.basename(p) for p in written) == sorted(t + ".wav" for t, _, _ in items)
-    # a0, a2, a4 share (target A, 61 frames): batches of 2 + 1; everything else runs alone
-    assert conv.stats == {"utterances": 7, "calls": 6, "audio_seconds": pytest.approx(sum(
-        torch.load(workdir / "units" / (os.path.basename(s)[:-4] + ".pt")).shape[1] for _, s, _ in items) / 50.0),
-        "targets": 2}
+    audio_s = sum(torch.load(workdir / "units" / (os.path.basename(s)[:-4] + ".pt")).shape[1] for _, s, _ in items) / 50.0
+    assert conv.stats["utterances"] == 7 and conv.stats["targets"] == 2 and conv.stats["audio_seconds"] == pytest.approx(audio_s)
+    if ragged:
+        # sorted lengths 25 33 61 61 61 61 140, at most 4 per call and 50 % padding: [25 33 61 61] [61 61 140]
+        assert conv.stats["calls"] == 2 and conv.stats["padded_audio_seconds"] == pytest.approx((4 * 61 + 3 * 140) / 50.0)
+    else:
+        # a0, a2, a4 share (target A, 61 frames): batches of 2 + 1; everything else runs alone
+        assert conv.stats["calls"] == 6 and conv.stats["padded_audio_seconds"] == pytest.approx(audio_s)
 
     checked_oracle = False
     for index, (title, src, tgt) in enumerate(items):
@@ -74,7 +79,7 @@ def test_convert_list_matches_single_clip_chain(workdir, sd, model_cfg, streams)
         noise = torch.randn((1, 192, unit.shape[2]), device=DEV, generator=gen)
         want = net.infer(unit, mel, noise=noise)[0, 0].cpu().numpy()
         assert got.shape == want.shape == (320 * unit.shape[2],)
-        assert np.array_equal(got, want), f"{title}: driver output differs from the single-clip call by {np.abs(got - want).max()}"
+        assert np.array_equal(got, want), f"{title}: driver output differs from the single-clip call by {np.abs(got - want).max()}"   # bit for bit, ragged batches included
         if not checked_oracle and title == "b5":
             mel_ref = mel_oracle.wave_to_mel(wav_t.double(), 1280, 80, 16000, 320, 1280, 0.0, None)
             ref = qvc_oracle.infer(sd, unit.cpu(), mel_ref.float(), noise.cpu(), dtype=torch.float64)[0, 0].numpy()
