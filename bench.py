@@ -317,7 +317,7 @@ def run_ours(args, rank, local_rank, world):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_note": traffic_note,
-        "kernel": "conv_tc_kernel + conv_tc2_kernel (tcgen05 implicit-GEMM series convolution; cta_group::1 and CTA-pair cta_group::2 variants)",
+        "kernel": "conv_tc_kernel + conv_tc2_kernel + conv_wn_kernel (tcgen05 implicit-GEMM series convolution: cta_group::1, CTA-pair cta_group::2, and the fused WN-layer variant)",
         "launches_per_step": int(conv_launches), "avg_launch_us": conv_ms_step * 1e3 / max(1, conv_launches),
         "kernel_ms_per_step": conv_ms_step, "kernel_share_of_step": conv_ms_step / ms,
         "flops_per_step": conv_flops,

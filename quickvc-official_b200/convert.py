@@ -94,6 +94,15 @@ def read_list(txtpath: str) -> List[Tuple[str, str, str]]:
     return items
 
 
+def shard_items(items: Sequence, rank: int, world: int) -> List:
+    """The share of rank `rank` out of `world` processes (one per GPU): every world-th line, so that long and short
+    utterances spread evenly whatever the order of the list.  Utterances are independent: no collective, every rank
+    writes its own files."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    return list(items[rank::world])
+
+
 def load_wave(path: str, sr: int) -> np.ndarray:
     """Mono float32 waveform at `sr` (the role of librosa.load at convert.py:62,65)."""
     from scipy.io import wavfile
@@ -361,11 +370,12 @@ class Converter:
             yield title, arr[b, 0, :320 * p.frames[b]]
 
     def convert_list(self, txtpath: str, outdir: str, *, use_timestamp: bool = False,
-                     noise_seed: Optional[int] = None) -> List[str]:
-        """convert.py:47-86: reads the list, converts, writes `<outdir>/<title>.wav`; returns the written paths."""
+                     noise_seed: Optional[int] = None, rank: int = 0, world: int = 1) -> List[str]:
+        """convert.py:47-86: reads the list, converts, writes `<outdir>/<title>.wav`; returns the written paths.
+        With `world` > 1 (one process per GPU) this rank converts every world-th line of the list."""
         os.makedirs(outdir, exist_ok=True)
         written = []
-        for title, audio in self.convert(read_list(txtpath), noise_seed=noise_seed):
+        for title, audio in self.convert(shard_items(read_list(txtpath), rank, world), noise_seed=noise_seed):
             name = f"{time.strftime('%m-%d_%H-%M', time.localtime())}_{title}.wav" if use_timestamp else f"{title}.wav"
             path = os.path.join(outdir, name)
             write_wave(path, self.hps.data.sampling_rate, audio)
@@ -400,6 +410,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     parser.add_argument("--seed", type=int, default=None, help="seed of the prior's noise draw (default: unseeded, as the reference)")
     args = parser.parse_args(argv)
 
+    # one process per GPU under torchrun: rank r converts lines r, r + world, ... on GPU LOCAL_RANK
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if "LOCAL_RANK" in os.environ:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     device = torch.device("cuda", torch.cuda.current_device())
     hps = get_hparams_from_file(args.hpfile)
     print("Loading model...")
@@ -410,7 +424,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
                      max_batch=args.max_batch, ragged=not args.no_ragged)
     print("Synthesizing...")
     t0 = time.perf_counter()
-    written = conv.convert_list(args.txtpath, args.outdir, use_timestamp=args.use_timestamp, noise_seed=args.seed)
+    written = conv.convert_list(args.txtpath, args.outdir, use_timestamp=args.use_timestamp, noise_seed=args.seed,
+                                rank=rank, world=world)
     dt = time.perf_counter() - t0
     print(f"{len(written)} files, {conv.stats['audio_seconds']:.1f} s of audio in {dt:.2f} s "
           f"({conv.stats['calls']} infer calls, {conv.stats['targets']} target speakers)")

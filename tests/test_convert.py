@@ -112,3 +112,13 @@ def test_converter_refuses_cpu():
     net = torch.nn.Linear(2, 2)
     with pytest.raises(RuntimeError, match="CUDA"):
         cv.Converter(net, cv.HParams(data={"sampling_rate": 16000}), units_dir=".")
+
+
+def test_shard_items_partitions_the_list():
+    items = [(f"t{i}", f"s{i}.wav", "tgt.wav") for i in range(11)]
+    for world in (1, 2, 3, 8, 16):
+        shares = [cv.shard_items(items, r, world) for r in range(world)]
+        assert sorted(sum(shares, [])) == sorted(items)
+        assert max(map(len, shares)) - min(map(len, shares)) <= 1
+    with pytest.raises(ValueError):
+        cv.shard_items(items, 2, 2)
