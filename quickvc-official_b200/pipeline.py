@@ -14,6 +14,67 @@ import torch
 from torch import Tensor
 
 
+class GraphedInfer:
+    """One `infer` call of fixed shape captured into a CUDA graph and replayed.
+
+    The ~110 kernel launches of a call (and the fork / join of the speaker-encoder side stream) become one graph
+    launch: the GPU-side time is unchanged -- the chain of dependent kernels is what a single clip costs
+    (profiles/r01_final_summary.md) -- but the host thread spends ~20 us per call instead of ~1 ms, which is what a
+    server multiplexing many streams needs.  Inputs are copied into static buffers; the returned waveform is the
+    graph's static output buffer (valid until the next call; clone it to keep it).
+    """
+
+    def __init__(self, net, batch: int, frames: int, *, mel_frames: int = 0, device: Optional[torch.device] = None) -> None:
+        """mel_frames > 0: `infer(unit, mel)` with a (1, 80, mel_frames) target mel; 0: `infer_with_embedding(unit, g)`
+        with `g` (1 | batch, 256) given at the first call (its batch size is then fixed)."""
+        self.net = net
+        self.device = device or next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphedInfer needs the module on a CUDA device")
+        d = self.device
+        self._unit = torch.zeros(batch, 256, frames, device=d)
+        self._noise = torch.zeros(batch, 192, frames, device=d)
+        self._mel = torch.zeros(1, 80, mel_frames, device=d) if mel_frames > 0 else None
+        self._g: Optional[Tensor] = None
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._wave: Optional[Tensor] = None
+
+    def _run(self) -> Tensor:
+        if self._mel is not None:
+            return self.net.infer(self._unit, self._mel, noise=self._noise)
+        return self.net.infer_with_embedding(self._unit, self._g, noise=self._noise)
+
+    def _capture(self) -> None:
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):           # warm-up outside the capture: weight folding, workspaces, attributes
+            self._run()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._wave = self._run()
+
+    @torch.no_grad()
+    def __call__(self, unit: Tensor, cond: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+        """`cond` is the target mel (mel_frames > 0) or the speaker embedding(s)."""
+        self._unit.copy_(unit, non_blocking=True)
+        if noise is None:
+            self._noise.normal_()                                   # models.py:94
+        else:
+            self._noise.copy_(noise, non_blocking=True)
+        if self._mel is not None:
+            self._mel.copy_(cond, non_blocking=True)
+        else:
+            cond = cond.reshape(cond.shape[0], -1)
+            if self._g is None:
+                self._g = torch.zeros_like(cond, device=self.device)
+            self._g.copy_(cond, non_blocking=True)
+        if self._graph is None:
+            self._capture()
+        self._graph.replay()
+        return self._wave
+
+
 class PipelinedConverter:
     """Converts a stream of host batches `(unit (B,256,T), mel (1,80,Tm))` to host waveforms `(B,1,320 T)`.
 

@@ -59,3 +59,25 @@ def test_one_full_length_utterance_against_oracle(big):
     ref = qvc_oracle.infer(sd, unit[b:b + 1], mel, noise[b:b + 1])
     err = float((wave[b:b + 1].cpu() - ref).abs().max())
     assert err < 1e-4, err            # north-star fp32-mode bound: max-abs waveform error 1e-4
+
+
+def test_one_minute_utterance_and_a_ragged_companion(big):
+    """A single 60 s utterance (T = 3000: 60000-row series in the decoder, 235 tiles per layer) against the oracle, and
+    the same utterance in a ragged batch next to a 7 s one."""
+    cfg, sd, _, mel, _ = big
+    net = SynthesizerTrn(641, 32, **cfg, precision="tf32").eval()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    T = 3000
+    unit, _, noise = synth.synthetic_inputs(2, T, 1, 8, 21)
+    u, m, n = unit.to(DEV), mel.to(DEV), noise.to(DEV)
+    long_alone = net.infer(u[:1], m, noise=n[:1])
+    assert long_alone.shape == (1, 1, 320 * T)
+    ref = qvc_oracle.infer(sd, unit[:1], mel, noise[:1])
+    assert float((long_alone.cpu() - ref).abs().max()) < 1e-4
+    lens = torch.tensor([T, 350])
+    both = net.infer(u, m, noise=n, lengths=lens)
+    assert float((both[0] - long_alone[0]).abs().max()) <= 2e-6
+    short_alone = net.infer(u[1:2, :, :350].contiguous(), m, noise=n[1:2, :, :350].contiguous())
+    assert float((both[1, 0, :320 * 350] - short_alone[0, 0]).abs().max()) <= 2e-6
+    assert float(both[1, 0, 320 * 350:].abs().max()) == 0.0

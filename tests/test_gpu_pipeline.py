@@ -8,7 +8,7 @@ import torch
 import synth
 from conftest import ROOT
 from quickvc_official_b200 import SynthesizerTrn
-from quickvc_official_b200.pipeline import PipelinedConverter
+from quickvc_official_b200.pipeline import GraphedInfer, PipelinedConverter
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -38,3 +38,25 @@ def test_pipelined_converter_matches_direct_calls():
     assert len(got) == n
     for g, w in zip(got, want):
         assert g.shape == (B, 1, 320 * T) and torch.equal(g, w)
+
+
+def test_graphed_infer_replays_the_same_arithmetic():
+    """A call captured into a CUDA graph (speaker-encoder fork / join included) gives the eager call's bits on new inputs."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "quickvc_model_config.json")))
+    shapes = {k: tuple(v) for k, v in json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_shapes.json"))).items()}
+    net = SynthesizerTrn(641, 32, **cfg).eval()
+    net.load_state_dict(synth.synthetic_state_dict(shapes, 0))
+    net = net.to(DEV)
+    B, T, TM = 2, 50, 200
+    graphed = GraphedInfer(net, B, T, mel_frames=TM)
+    cached = GraphedInfer(net, B, T)
+    for seed in (1, 2, 3):
+        unit, mel, noise = (t.to(DEV) for t in synth.synthetic_inputs(B, T, 1, TM, seed))
+        want = net.infer(unit, mel, noise=noise)
+        got = graphed(unit, mel, noise)
+        assert torch.equal(got, want)
+        g = net.embed_speaker(mel)
+        assert torch.equal(cached(unit, g, noise), net.infer_with_embedding(unit, g, noise=noise))
+    # without a supplied noise the draw happens inside the static buffer: finite output of the right shape
+    out = graphed(unit, mel)
+    assert out.shape == (B, 1, 320 * T) and bool(torch.isfinite(out).all())
