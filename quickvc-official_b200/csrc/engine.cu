@@ -132,11 +132,12 @@ int run(const Ctx& c, const qvc_conv_args& a) { return qvc_conv1d(&a, (qvc_strea
 // convolution reads anyway (qvc_epi_segment.res_op): the c2 layers are memory-bound there and this halves their
 // traffic.  In the fp32 (TF32) mode the residual streams stay unrounded fp32.
 bool residual_from_operand(const Ctx& c) {
-  static const bool enabled = [] {
+  static const int mode = [] {                    // 0: never, 1 (default): bf16 mode, 2: experiment -- TF32 mode too
     const char* e = getenv("QVC_RES_FROM_OP");
-    return !(e && e[0] == '0');
+    return e ? atoi(e) : 1;
   }();
-  return enabled && c.m->opformat == QVC_OPF_BF16 && c.m->backend == QVC_BACKEND_TCGEN05;
+  if (c.m->backend != QVC_BACKEND_TCGEN05) return false;
+  return (mode >= 1 && c.m->opformat == QVC_OPF_BF16) || (mode >= 2 && c.m->opformat == QVC_OPF_TF32);
 }
 
 // One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack

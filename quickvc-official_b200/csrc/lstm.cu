@@ -2,9 +2,11 @@
 //
 // Per layer: (1) the input projection W_ih x_t + b for every step at once (one exact-fp32 series
 // GEMM), (2) a persistent recurrent kernel: a thread-block cluster of 8 CTAs keeps the layer's
-// 1 MB W_hh resident in shared memory (128 KB slice = 32 hidden units x 4 gates per CTA) for all
-// steps; each step every CTA computes its 32 units for up to 8 sequences, pushes the new h slice
-// into the other CTAs' shared memory (DSMEM) and the cluster barrier closes the step.
+// 1 MB W_hh resident on chip (32 hidden units x 4 gates per CTA, in registers) for all steps; each
+// step every CTA computes its 32 units for up to 8 sequences and pushes the new h slice into all 8
+// CTAs' shared memory with st.async, whose bytes complete a transaction mbarrier in the receiving CTA:
+// a step is closed by data arrival, not by a cluster barrier (whose release fence also waited for the
+// step's global stores and prefetches: ~1 us of every 2.7 us step, profiles/r01_final_summary.md).
 // (3) a small finishing kernel: Linear, ReLU, L2-normalise, mean over the windows.
 // All arithmetic is fp32 FMA: the recurrence amplifies operand rounding, and the whole encoder is
 // 2.4 % of the path's FLOPs.
@@ -27,7 +29,37 @@ constexpr int UNITS_PER_CTA = HID / CLUSTER;   // 32
 constexpr int MAXSEQ = 8;                      // sequences per cluster
 constexpr int REC_THREADS = 256;
 constexpr size_t REC_SMEM = (size_t)UNITS_PER_CTA * 4 * HID * sizeof(float)      // W_hh slice
-                            + (size_t)2 * MAXSEQ * HID * sizeof(float);          // h double buffer
+                            + (size_t)2 * MAXSEQ * HID * sizeof(float)           // h double buffer
+                            + 16;                                                // one mbarrier per h buffer
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 4 bytes into a CTA of the cluster; the write completes 4 bytes of the transaction count of `mbar` (same CTA)
+__device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "r"(__float_as_uint(v)), "r"(cluster_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {          // bounded: a protocol bug must trap, not hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
 
 struct RecParams {
   const float* w_hh;      // (1024, 256)
@@ -40,19 +72,24 @@ struct RecParams {
   float* hlast;           // [nseq][256] or NULL
 };
 
+// NS = sequences a cluster carries (compile time: the per-step loop has no branches, so the h loads of all k slices
+// are scheduled ahead of the FMAs that use them -- with a runtime count every (k slice, sequence) block was a
+// branch + LDS + dependent FMAs and the step was one long latency chain, ~4100 cycles for ~650 instructions per warp).
+template <int NS>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(REC_THREADS, 1)
 lstm_recurrent_kernel(const RecParams p) {
   extern __shared__ __align__(16) float smem[];
   float* Wsm = smem;                                        // [32 units][4 gates][256]
   float* hbuf = smem + UNITS_PER_CTA * 4 * HID;             // [2][MAXSEQ][256]
+  const uint32_t mbar = smem_addr(hbuf + 2 * MAXSEQ * HID);  // [2]: h buffer b is complete when mbar[b]'s phase is
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int group = blockIdx.x / CLUSTER;                   // which block of <= 8 sequences
-  const int s_base = group * p.spc;
-  const int ns = min(p.spc, p.nseq - s_base);
+  const int group = blockIdx.x / CLUSTER;                   // which block of <= NS sequences
+  const int s_base = group * NS;
+  const int ns = min(NS, p.nseq - s_base);
   const int tid = threadIdx.x;
-  const int ks = tid & 7;                                   // k-slice / sequence owned in the update
+  const int ks = tid & 7;                                   // k-slice of the matrix-vector product
   const int u = tid >> 3;                                   // local hidden unit
   const int U = rank * UNITS_PER_CTA + u;                   // global hidden unit
 
@@ -66,20 +103,33 @@ lstm_recurrent_kernel(const RecParams p) {
     *reinterpret_cast<float4*>(Wsm + ((uu * 4 + g) * HID) + 4 * k4) = v;
   }
   for (int i = tid; i < 2 * MAXSEQ * HID; i += REC_THREADS) hbuf[i] = 0.f;
+  // every step, each of the 8 CTAs sends this CTA 32 units x ns sequences x 4 bytes
+  const uint32_t step_bytes = (uint32_t)(CLUSTER * UNITS_PER_CTA * ns * sizeof(float));
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
-  // sequence owned by this lane in the cell update
-  const int s_own = ks;
-  const bool own = s_own < ns;
+  // The 8 k-slice lanes of a unit reduce-scatter their partial sums (below): with NS sequences the lane whose low
+  // log2(8 / NS) bits are zero ends up owning sequence ks / (8 / NS) and performs its cell update.
+  constexpr int LANES_PER_SEQ = 8 / NS;
+  const int s_own = ks / LANES_PER_SEQ;
+  const bool own = (ks % LANES_PER_SEQ) == 0 && s_own < ns;
   int64_t gx_row0 = 0;
   if (own) {
     const int sg = s_base + s_own;
     gx_row0 = (p.last_row >= 0 && sg == p.nseq - 1) ? p.last_row : (int64_t)sg * p.row_stride;
   }
   float c_state = 0.f;
-  float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+  float gxv[4] = {0.f, 0.f, 0.f, 0.f}, gxn[4] = {0.f, 0.f, 0.f, 0.f};     // this step's / the next step's input projection
   if (own) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) gxv[g] = __ldg(p.gx + gx_row0 * GATES + g * HID + U);
+    if (p.steps > 1) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gxn[g] = __ldg(p.gx + (gx_row0 + 1) * GATES + g * HID + U);
+    }
   }
   cluster.sync();
 
@@ -92,78 +142,95 @@ lstm_recurrent_kernel(const RecParams p) {
     for (int kk = 0; kk < HID / 32; ++kk)
       wreg[g][kk] = *reinterpret_cast<const float4*>(Wsm + (u * 4 + g) * HID + kk * 32 + ks * 4);
 
-  float* remote[CLUSTER];
+  uint32_t remote_h[CLUSTER], remote_bar[CLUSTER];
 #pragma unroll
-  for (int r = 0; r < CLUSTER; ++r) remote[r] = cluster.map_shared_rank(hbuf, r);
+  for (int r = 0; r < CLUSTER; ++r) {
+    remote_h[r] = map_rank(smem_addr(hbuf), (uint32_t)r);
+    remote_bar[r] = map_rank(mbar, (uint32_t)r);
+  }
 
   for (int t = 0; t < p.steps; ++t) {
+    // h_t is in buffer t & 1: zeros for t = 0, else complete once all 8 CTAs' slices of step t-1 have landed
+    // (phase (t-1) >> 1 of that buffer's barrier).  Then arm the other buffer's barrier for h_{t+1}: nobody can
+    // send h_{t+1} before this CTA has sent its part of it, below.
+    if (t > 0) mbar_wait_parity(mbar + 8 * (t & 1), (uint32_t)(((t - 1) >> 1) & 1));
+    if (tid == 0 && t + 1 < p.steps) mbar_expect(mbar + 8 * ((t + 1) & 1), step_bytes);
     const float* hc = hbuf + (t & 1) * MAXSEQ * HID;
-    float acc[4][MAXSEQ];
+    float acc[4][NS];
 #pragma unroll
     for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int s = 0; s < MAXSEQ; ++s) acc[g][s] = 0.f;
+      for (int s = 0; s < NS; ++s) acc[g][s] = 0.f;
 
+    // rows of sequences past ns are never written: they stay zero
 #pragma unroll
     for (int kk = 0; kk < HID / 32; ++kk) {
       const int k = kk * 32 + ks * 4;
 #pragma unroll
-      for (int s = 0; s < MAXSEQ; ++s) {
-        if (s < ns) {
-          const float4 hv = *reinterpret_cast<const float4*>(hc + s * HID + k);
+      for (int s = 0; s < NS; ++s) {
+        const float4 hv = *reinterpret_cast<const float4*>(hc + s * HID + k);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            acc[g][s] = fmaf(wreg[g][kk].x, hv.x, acc[g][s]);
-            acc[g][s] = fmaf(wreg[g][kk].y, hv.y, acc[g][s]);
-            acc[g][s] = fmaf(wreg[g][kk].z, hv.z, acc[g][s]);
-            acc[g][s] = fmaf(wreg[g][kk].w, hv.w, acc[g][s]);
-          }
+        for (int g = 0; g < 4; ++g) {
+          acc[g][s] = fmaf(wreg[g][kk].x, hv.x, acc[g][s]);
+          acc[g][s] = fmaf(wreg[g][kk].y, hv.y, acc[g][s]);
+          acc[g][s] = fmaf(wreg[g][kk].z, hv.z, acc[g][s]);
+          acc[g][s] = fmaf(wreg[g][kk].w, hv.w, acc[g][s]);
         }
       }
     }
-    // reduce-scatter over the 8 k-slice lanes: lane ks ends with the full sums of sequence ks
+    // reduce(-scatter) over the 8 k-slice lanes, bit 2 then 1 then 0 of ks: while more than one sequence is left a
+    // stage halves the sequences a lane keeps (the kept half chosen by that bit), afterwards it is a plain sum
     float gate[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      float v4[4], v2[2];
+      float v[NS];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float keep = (ks & 4) ? acc[g][4 + i] : acc[g][i];
-        const float send = (ks & 4) ? acc[g][i] : acc[g][4 + i];
-        v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
+      for (int i = 0; i < NS; ++i) v[i] = acc[g][i];
+      int n = NS;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float keep = (ks & 2) ? v4[2 + i] : v4[i];
-        const float send = (ks & 2) ? v4[i] : v4[2 + i];
-        v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      for (int bit = 4; bit >= 1; bit >>= 1) {
+        if (n > 1) {
+          const int half = n >> 1;
+#pragma unroll
+          for (int i = 0; i < NS / 2; ++i) {
+            if (i < half) {
+              const float keep = (ks & bit) ? v[half + i] : v[i];
+              const float send = (ks & bit) ? v[i] : v[half + i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+          }
+          n = half;
+        } else {
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+        }
       }
-      {
-        const float keep = (ks & 1) ? v2[1] : v2[0];
-        const float send = (ks & 1) ? v2[0] : v2[1];
-        gate[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-      }
+      gate[g] = v[0];
     }
-    float h_new = 0.f;
     if (own) {
       const float ig = sigmoid_acc(gate[0] + gxv[0]);
       const float fg = sigmoid_acc(gate[1] + gxv[1]);
       const float gg = tanhf(gate[2] + gxv[2]);
       const float og = sigmoid_acc(gate[3] + gxv[3]);
       c_state = fg * c_state + ig * gg;
-      h_new = og * tanhf(c_state);
-      const int off = ((t + 1) & 1) * MAXSEQ * HID + s_own * HID + U;
+      const float h_new = og * tanhf(c_state);
+      if (t + 1 < p.steps) {
+        const uint32_t off = (uint32_t)((((t + 1) & 1) * MAXSEQ * HID + s_own * HID + U) * sizeof(float));
+        const uint32_t boff = 8u * (uint32_t)((t + 1) & 1);
 #pragma unroll
-      for (int r = 0; r < CLUSTER; ++r) remote[r][off] = h_new;
+        for (int r = 0; r < CLUSTER; ++r) st_async_f32(remote_h[r] + off, h_new, remote_bar[r] + boff);
+      }
       if (p.hseq) p.hseq[((int64_t)(s_base + s_own) * p.steps + t) * HID + U] = h_new;
       if (p.hlast && t == p.steps - 1) p.hlast[(int64_t)(s_base + s_own) * HID + U] = h_new;
-      if (t + 1 < p.steps) {
+      // input projection two steps ahead: an L2 round trip is longer than one step
 #pragma unroll
-        for (int g = 0; g < 4; ++g) gxv[g] = __ldg(p.gx + (gx_row0 + t + 1) * GATES + g * HID + U);
+      for (int g = 0; g < 4; ++g) gxv[g] = gxn[g];
+      if (t + 2 < p.steps) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gxn[g] = __ldg(p.gx + (gx_row0 + t + 2) * GATES + g * HID + U);
       }
     }
-    cluster.sync();
   }
+  cluster.sync();          // no CTA may exit while a peer could still be writing into its shared memory
 }
 
 // emb[w][n] = normalise(relu(lin_w h[w] + lin_b))   (models.py:517-518): one CTA per window
@@ -270,7 +337,10 @@ extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm,
 
   static bool attr_set = false;
   if (!attr_set) {
-    QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
     attr_set = true;
   }
 
@@ -301,11 +371,16 @@ extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm,
     // dependent steps (per-step FMA work is proportional to the sequences of a cluster).  Default 2 per cluster:
     // one 10 s target mel = 7 windows = 4 clusters = 32 SMs for ~0.9 ms instead of 8 SMs for 1.7 ms, which keeps the
     // encoder off the critical path of the step (it runs beside the prior encoder and the flow waits for it).
-    int spc = 2;
-    if (const char* e = getenv("QVC_SPK_SPC")) { const int v = atoi(e); if (v >= 1 && v <= MAXSEQ) spc = v; }
+    int spc = pl.nseq == 1 ? 1 : 2;
+    if (const char* e = getenv("QVC_SPK_SPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) spc = v; }
     rp.spc = spc;
     const int groups = (pl.nseq + spc - 1) / spc;
-    lstm_recurrent_kernel<<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp);
+    switch (spc) {
+      case 1:  lstm_recurrent_kernel<1><<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp); break;
+      case 2:  lstm_recurrent_kernel<2><<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp); break;
+      case 4:  lstm_recurrent_kernel<4><<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp); break;
+      default: lstm_recurrent_kernel<8><<<groups * CLUSTER, REC_THREADS, REC_SMEM, stream>>>(rp); break;
+    }
     QVC_PROPAGATE(post_launch("lstm_recurrent_kernel"));
   }
   float* emb = reinterpret_cast<float*>(ws + pl.off_emb);

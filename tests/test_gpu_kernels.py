@@ -253,7 +253,11 @@ def test_tail_matches_oracle(frames, batch, sd):
 
 
 @pytest.mark.parametrize("bm,tm", [(1, 129), (1, 250), (1, 500), (1, 1500), (3, 100), (1, 128), (9, 7)])
-def test_speaker_encoder_matches_oracle(bm, tm, sd):
+@pytest.mark.parametrize("spc", [None, 1, 4, 8])
+def test_speaker_encoder_matches_oracle(bm, tm, spc, sd, monkeypatch):
+    # spc = sequences (windows) per LSTM cluster: one template instance of the recurrent kernel each
+    if spc is not None:
+        monkeypatch.setenv("QVC_SPK_SPC", str(spc))
     lib = capi.load()
     f = fold.fold_state_dict({k: v for k, v in sd.items() if not k.startswith("enc_q.")}, capi.OPF_F32)
     t = {k: v.to(DEV) for k, v in f.tensors.items() if k.startswith("spk.")}
