@@ -432,7 +432,8 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
   int spk_sms = 0;
   if (with_spk) {
     const int nseq = mel_frames > 128 ? (mel_frames - 128 + 63) / 64 + 1 : mel_batch;
-    spk_sms = 8 * ((nseq + 1) / 2);                 // lstm.cu: two sequences per 8-CTA cluster
+    const int spc = spk_sequences_per_cluster(nseq);
+    spk_sms = 8 * ((nseq + spc - 1) / spc);         // one 8-CTA cluster per spc windows (lstm.cu)
     if (spk_sms > 64) spk_sms = 64;
   }
 

@@ -14,6 +14,7 @@ int cond_vectors(const float* w, const float* bias, const float* g, int n_embed,
                  cudaStream_t stream);
 int reflect_row(void* base, int64_t bstride_bytes, int row_bytes, int batch, cudaStream_t stream);
 
+int spk_sequences_per_cluster(int nseq);   // lstm.cu: windows one 8-CTA LSTM cluster carries
 void tc_reserve_sms(int n);         // conv_tc.cu: SMs the persistent convolution grids leave free (per host thread)
 
 }  // namespace qvc

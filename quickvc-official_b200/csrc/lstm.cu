@@ -307,6 +307,12 @@ SpkPlan make_plan(int bm, int tm) {
 
 }  // namespace
 
+int spk_sequences_per_cluster(int nseq) {
+  int spc = nseq <= 4 ? 1 : 2;
+  if (const char* e = getenv("QVC_SPK_SPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) spc = v; }
+  return spc;
+}
+
 }  // namespace qvc
 
 extern "C" size_t qvc_spk_workspace_bytes(int bm, int tm) {
@@ -368,11 +374,10 @@ extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm,
     rp.hseq = layer < 2 ? hseq : nullptr;
     rp.hlast = layer == 2 ? hlast : nullptr;
     // Sequences (windows) are independent: spreading them over more clusters shortens every one of the 384
-    // dependent steps (per-step FMA work is proportional to the sequences of a cluster).  Default 2 per cluster:
-    // one 10 s target mel = 7 windows = 4 clusters = 32 SMs for ~0.9 ms instead of 8 SMs for 1.7 ms, which keeps the
-    // encoder off the critical path of the step (it runs beside the prior encoder and the flow waits for it).
-    int spc = pl.nseq == 1 ? 1 : 2;
-    if (const char* e = getenv("QVC_SPK_SPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) spc = v; }
+    // dependent steps (per-step FMA work is proportional to the sequences of a cluster).  spk_sequences_per_cluster():
+    // one window per cluster up to 4 windows (a 5 s target mel = 3 windows = 24 SMs), two beyond (10 s = 7 windows =
+    // 32 SMs), which keeps the encoder hidden behind the prior encoder it runs beside, for single clips too.
+    const int spc = spk_sequences_per_cluster(pl.nseq);
     rp.spc = spc;
     const int groups = (pl.nseq + spc - 1) / spc;
     switch (spc) {
