@@ -124,7 +124,12 @@ typedef struct {
    * the end of that utterance alone.  fp32 outputs (raw, aux) past the count are unspecified. */
   const int32_t* live_units; /* device, [batch], or NULL                                       */
   int32_t    live_mul;
-  int32_t    _pad3;
+  /* Structured zeros of the filter (a hint: results never depend on it).  When tap_split > 0, the block of w
+   * with output columns in half p (p = n >= cout/2), input channels in half q (q = c >= tap_split) and tap j
+   * is all zero unless tap_lo[p][q] <= j <= tap_hi[p][q]; kernels may skip such blocks.  Every range must be
+   * non-empty.  Used by the frame-paired form of the 128-channel MRF layers (see qvc_model.paired). */
+  int32_t    tap_split;
+  int32_t    tap_lo[2][2], tap_hi[2][2];
 } qvc_conv_args;
 
 int qvc_conv1d(const qvc_conv_args* args, qvc_stream_t stream);
@@ -236,6 +241,14 @@ typedef struct {
   int32_t backend;          /* qvc_backend                                                      */
   int32_t chunk_utts;       /* decoder sub-batch (utterances) kept L2-resident; 0 = auto        */
   qvc_layer layers[QVC_NUM_LAYERS];
+  /* Frame-paired form of a layer (w == NULL: none), for dilation-1 layers with 128 input and output channels
+   * (MRF-2, modules.py:133-144): two consecutive frames are one row of a series with 2 x 128 channels,
+   *   out'[n][p*128 + c] = out[2n + p][c],   x'[m][q*128 + ci] = x[2m + q][ci]
+   * -- the same memory, row pitch doubled -- which turns the k-tap 128 -> 128 convolution into a
+   * (k+1)/2+1-tap 256 -> 256 one whose filter w'[p*128+c][a][q*128+ci] = w[c][2a + q - p + pad][ci] is zero outside
+   * k + 1 of its (tap, input half) blocks.  256 output rows let a CTA pair issue M = 256 MMAs at the full tensor rate
+   * where the 128-row form is capped at 2/3 by its shared-memory operand reads. */
+  qvc_layer paired[QVC_NUM_LAYERS];
   /* speaker conditioning folded to per-utterance bias vectors:
    * cond_w :: [cond_rows][256] fp32, cond_b :: [cond_rows] fp32 where the rows are
    * 4 couplings x (4 layers x 384) gate biases (cond_layer + in_layer bias, modules.py:83-96)

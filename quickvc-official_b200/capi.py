@@ -45,7 +45,8 @@ class ConvArgs(C.Structure):
                 ("seg", EpiSegment * 2),
                 ("noise", Tensor), ("aux0", Tensor), ("aux1", Tensor),
                 ("opformat", C.c_int32), ("backend", C.c_int32),
-                ("live_units", C.c_void_p), ("live_mul", C.c_int32), ("_pad3", C.c_int32)]
+                ("live_units", C.c_void_p), ("live_mul", C.c_int32), ("tap_split", C.c_int32),
+                ("tap_lo", (C.c_int32 * 2) * 2), ("tap_hi", (C.c_int32 * 2) * 2)]
 
 
 class SpkWeights(C.Structure):
@@ -70,7 +71,7 @@ class Layer(C.Structure):
 class Model(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("opformat", C.c_int32), ("backend", C.c_int32),
                 ("chunk_utts", C.c_int32),
-                ("layers", Layer * QVC_NUM_LAYERS),
+                ("layers", Layer * QVC_NUM_LAYERS), ("paired", Layer * QVC_NUM_LAYERS),
                 ("cond_w", C.c_void_p), ("cond_b", C.c_void_p), ("cond_rows", C.c_int32), ("_pad", C.c_int32),
                 ("spk", SpkWeights), ("tail", TailWeights)]
 

@@ -53,6 +53,12 @@ struct alignas(64) TcParams {
   int32_t slab_boxes, slab_box_rows;       // slab = slab_boxes TMA boxes of slab_box_rows frames
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes, w_stage_bytes;
+  // structured zeros of the filter (qvc_conv_args.tap_split): group gi's chunks lie in output half gp[gi] (2 = both),
+  // channel chunks from split_chunk on are input half 1; block (tap j) is skipped outside [jlo[p][q], jhi[p][q]]
+  // (row 2 of the tables = the union over both output halves).  Without a hint every range is [0, k-1].
+  int32_t split_chunk;
+  int32_t gp[MAXGROUPS];
+  int32_t jlo[3][2], jhi[3][2];
   int32_t debug;                           // diagnostics only (QVC_TC_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue I/O
   EpiParams ep;
 };
@@ -126,7 +132,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             tma_load_3d(slab0 + s * p.slab_stage_bytes + i * p.slab_box_rows * ROW_BYTES, &p.mx, full_slab + 8 * s,
                         cc * KC, t0 - p.pad_left + i * p.slab_box_rows, b);
           if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
-          for (int j = 0; j < p.k; ++j) {
+          const int qh = cc >= p.split_chunk ? 1 : 0;
+          for (int j = p.jlo[p.gp[gi]][qh]; j <= p.jhi[p.gp[gi]][qh]; ++j) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
             if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
             else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
@@ -159,11 +166,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       for (int cc = 0; cc < n_cchunks; ++cc) {
         mbar_wait(full_slab + 8 * s, ph);
         const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-        for (int j = 0; j < p.k; ++j) {
+        const int qh = cc >= p.split_chunk ? 1 : 0;
+        const int jfirst = p.jlo[p.gp[gi]][0], jlast = p.jhi[p.gp[gi]][qh];
+        for (int j = p.jlo[p.gp[gi]][qh]; j <= jlast; ++j) {
           mbar_wait(full_w + 8 * ws, wph);
           tc_fence_after();
           const uint32_t wst = w0 + ws * p.w_stage_bytes;
-          const uint32_t first = (cc | j) == 0 ? 0u : 1u;
+          const uint32_t first = (cc == 0 && j == jfirst) ? 0u : 1u;
           const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
           if (elect_one()) {
             for (int ci = 0; ci < gs; ++ci) {
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               }
             }
             tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
-            if (j == p.k - 1) tc_commit(empty_slab + 8 * s);
+            if (j == jlast) tc_commit(empty_slab + 8 * s);
           }
           __syncwarp();
           if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
@@ -454,6 +463,28 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
         p.row0[gi][ci] = r0;
         p.valid[gi][ci] = a.cout - r0 < CHUNK_M ? a.cout - r0 : CHUNK_M;
       }
+    }
+  }
+  // structured-zero hint -> per-group tap ranges
+  p.split_chunk = 1 << 30;
+  for (int pp = 0; pp < 3; ++pp)
+    for (int q = 0; q < 2; ++q) { p.jlo[pp][q] = 0; p.jhi[pp][q] = a.k - 1; }
+  for (int gi = 0; gi < p.ngroups; ++gi) p.gp[gi] = 2;
+  if (a.tap_split > 0 && a.tap_split % kc == 0 && a.tap_split < a.cin && !paired && (a.cout / 2) % CHUNK_M == 0) {
+    p.split_chunk = a.tap_split / kc;
+    for (int q = 0; q < 2; ++q) {
+      for (int pp = 0; pp < 2; ++pp) {
+        p.jlo[pp][q] = a.tap_lo[pp][q]; p.jhi[pp][q] = a.tap_hi[pp][q];
+        QVC_REQUIRE(p.jlo[pp][q] >= 0 && p.jhi[pp][q] < a.k && p.jlo[pp][q] <= p.jhi[pp][q],
+                    "conv1d: bad tap range [%d, %d] for k = %d", p.jlo[pp][q], p.jhi[pp][q], a.k);
+      }
+      p.jlo[2][q] = p.jlo[0][q] < p.jlo[1][q] ? p.jlo[0][q] : p.jlo[1][q];
+      p.jhi[2][q] = p.jhi[0][q] > p.jhi[1][q] ? p.jhi[0][q] : p.jhi[1][q];
+    }
+    for (int gi = 0; gi < p.ngroups; ++gi) {
+      const int first_half = p.row0[gi][0] >= a.cout / 2 ? 1 : 0;
+      const int last_half = p.row0[gi][p.gsize[gi] - 1] >= a.cout / 2 ? 1 : 0;
+      p.gp[gi] = first_half == last_half ? first_half : 2;
     }
   }
   int ntime = (ACC_COLS / g) & ~31;

@@ -39,6 +39,10 @@ struct alignas(64) Tc2Params {
   int32_t slab_box_rows;                   // one TMA box per slab (128 + halo <= 256 rows)
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes;
+  // structured zeros of the filter (qvc_conv_args.tap_split): channel chunks from split_chunk on use taps
+  // [jlo[1], jhi[1]], the ones before it [jlo[0], jhi[0]]; without a hint both ranges are [0, k-1]
+  int32_t split_chunk;
+  int32_t jlo[2], jhi[2];
   EpiParams ep;
 };
 
@@ -162,7 +166,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           if (leader) mbar_expect_tx(full_slab + 8 * s, 2 * slab_bytes);       // bytes of both CTAs
           tma2_load_3d(slab0 + s * p.slab_stage_bytes, &p.mx, lead_full_slab + 8 * s, cc * KC, t0 - p.pad_left, b);
           if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
-          for (int j = 0; j < p.k; ++j) {
+          const int qh = cc >= p.split_chunk ? 1 : 0;
+          for (int j = p.jlo[qh]; j <= p.jhi[qh]; ++j) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
             if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * w_stage_bytes);
             tma2_load_2d(w0 + ws * w_stage_bytes, &p.mw, lead_full_w + 8 * ws, j * p.cin + cc * KC, wrow);
@@ -190,10 +195,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         for (int cc = 0; cc < n_cchunks; ++cc) {
           mbar_wait(full_slab + 8 * s, ph);
           const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-          for (int j = 0; j < p.k; ++j) {
+          const int qh = cc >= p.split_chunk ? 1 : 0;
+          const int jlast = p.jhi[qh];
+          for (int j = p.jlo[qh]; j <= jlast; ++j) {
             mbar_wait(full_w + 8 * ws, wph);
             tc_fence_after();
-            const uint32_t first = (cc | j) == 0 ? 0u : 1u;
+            const uint32_t first = (cc == 0 && j == p.jlo[0]) ? 0u : 1u;
             const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
             const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * w_stage_bytes) & 0x3FFFFu) >> 4);
             if (elect_one()) {
@@ -206,7 +213,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
                   umma2<OPF>(d + (uint32_t)PN, adesc + (CHUNK_BYTES >> 4) + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
               }
               tc2_commit(empty_w + 8 * ws);
-              if (j == p.k - 1) tc2_commit(empty_slab + 8 * s);
+              if (j == jlast) tc2_commit(empty_slab + 8 * s);
             }
             __syncwarp();
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
@@ -358,6 +365,19 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   Tc2Params p{};
   QVC_PROPAGATE(build_epi_params(a, &p.ep));
   p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
+  // structured-zero hint: a pair tile holds both output halves, so a (tap, input half) block is skipped only when it
+  // is zero for both of them
+  p.split_chunk = 1 << 30;
+  p.jlo[0] = p.jlo[1] = 0;
+  p.jhi[0] = p.jhi[1] = a.k - 1;
+  if (a.tap_split > 0 && a.tap_split % kc == 0 && a.tap_split < a.cin && a.epilogue == QVC_EPI_LINEAR) {
+    p.split_chunk = a.tap_split / kc;
+    for (int q = 0; q < 2; ++q) {
+      p.jlo[q] = a.tap_lo[0][q] < a.tap_lo[1][q] ? a.tap_lo[0][q] : a.tap_lo[1][q];
+      p.jhi[q] = a.tap_hi[0][q] > a.tap_hi[1][q] ? a.tap_hi[0][q] : a.tap_hi[1][q];
+      QVC_REQUIRE(p.jlo[q] >= 0 && p.jhi[q] < a.k && p.jlo[q] <= p.jhi[q], "conv1d: bad tap range [%d, %d] for k = %d", p.jlo[q], p.jhi[q], a.k);
+    }
+  }
   p.pair_n = pair_n;
   p.nacc = gate ? 2 : 1;
   p.nbuf = p.nacc * pair_n > ACC_COLS ? 1 : 2;

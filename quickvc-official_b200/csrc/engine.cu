@@ -128,6 +128,40 @@ qvc_conv_args layer_args(const Ctx& c, int li, qvc_tensor x, int batch, int x_ro
 
 int run(const Ctx& c, const qvc_conv_args& a) { return qvc_conv1d(&a, (qvc_stream_t)c.st); }
 
+// Frame-paired form of a dilation-1, 128-channel layer (qvc_model.paired): used whenever it exists, whatever the
+// batch, so that an utterance's samples do not depend on what it is batched with (the summation order inside a
+// dot product differs between the two forms).
+bool use_frame_pairs(const Ctx& c, int li, int rows) {
+  const char* e = getenv("QVC_FRAME_PAIR");          // read per call: tests switch it
+  const bool enabled = !(e && e[0] == '0');
+  return enabled && c.m->backend == QVC_BACKEND_TCGEN05 && c.m->paired[li].w != nullptr && rows % 2 == 0;
+}
+
+// arguments of layer li in frame-paired form: x holds `rows` frames of `ch` channels with row pitch ch
+qvc_conv_args paired_args(const Ctx& c, int li, const void* x, int64_t bs, int batch, int rows, int ch) {
+  const qvc_layer& L = c.m->paired[li];
+  const qvc_layer& L0 = c.m->layers[li];
+  qvc_conv_args a{};
+  a.x = tens(x, bs, 2 * ch); a.batch = batch; a.x_rows = rows / 2; a.out_rows = rows / 2;
+  a.cin = L.cin; a.w = L.w; a.bias = L.bias; a.bias_bstride = 0;
+  a.cout = L.cout; a.k = L.k; a.dil = 1; a.pad_left = L.pad_left;
+  a.epilogue = QVC_EPI_LINEAR; a.nseg = 1;
+  a.opformat = c.m->opformat; a.backend = c.m->backend;
+  if (c.lengths && (rows / 2) % c.T == 0) { a.live_units = c.lengths; a.live_mul = (rows / 2) / c.T; }
+  // w'[p C + c][a][q cin + ci] = w[c][2 (a - pad') + q - p + pad][ci]: non-zero for 0 <= 2 (a - pad') + q - p + pad < k
+  a.tap_split = ch;
+  for (int p = 0; p < 2; ++p)
+    for (int q = 0; q < 2; ++q) {
+      const int off = p - q - L0.pad_left;                       // need 0 <= 2 a0 - off < k with a0 = a - pad'
+      const int lo = off >= 0 ? (off + 1) / 2 : -((-off) / 2);    // ceil(off / 2)
+      const int hi_num = L0.k - 1 + off;                         // floor((k - 1 + off) / 2)
+      const int hi = hi_num >= 0 ? hi_num / 2 : -((-hi_num + 1) / 2);
+      a.tap_lo[p][q] = lo + L.pad_left;
+      a.tap_hi[p][q] = hi + L.pad_left;
+    }
+  return a;
+}
+
 // bf16 mode on the tensor-core back end keeps the residual streams of the MRF only as the operand copy the next
 // convolution reads anyway (qvc_epi_segment.res_op): the c2 layers are memory-bound there and this halves their
 // traffic.  In the fp32 (TF32) mode the residual streams stay unrounded fp32.
@@ -197,34 +231,40 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
     const float* srcR = x1R;
     const void* srcO = x1O;
     for (int j = 0; j < 3; ++j) {
-      qvc_conv_args a = layer_args(c, lb + j, tens(srcO, bs, ch), cb, rows, rows);
-      a.seg[0] = seg(0, ch);
+      // frame-paired layers see every tensor as [rows / 2][2 ch]: the same memory with the row pitch doubled
+      const bool p1 = use_frame_pairs(c, lb + j, rows), p2 = use_frame_pairs(c, lb + 3 + j, rows);
+      const int w1 = p1 ? 2 * ch : ch, w2 = p2 ? 2 * ch : ch;
+      qvc_conv_args a = p1 ? paired_args(c, lb + j, srcO, bs, cb, rows, ch)
+                           : layer_args(c, lb + j, tens(srcO, bs, ch), cb, rows, rows);
+      a.seg[0] = seg(0, w1);
       a.seg[0].slope = 0.1f;
-      a.seg[0].op = tens(tO, bs, ch);
+      a.seg[0].op = tens(tO, bs, w1);
       QVC_PROPAGATE(run(c, a));
 
-      qvc_conv_args d = layer_args(c, lb + 3 + j, tens(tO, bs, ch), cb, rows, rows);
-      d.seg[0] = seg(0, ch);
+      qvc_conv_args d = p2 ? paired_args(c, lb + 3 + j, tO, bs, cb, rows, ch)
+                           : layer_args(c, lb + 3 + j, tens(tO, bs, ch), cb, rows, rows);
+      d.seg[0] = seg(0, w2);
       if (rfo) {
-        d.seg[0].res_op = tens(srcO, bs, ch);       // leaky_relu(x, 0.1) in operand format
+        d.seg[0].res_op = tens(srcO, bs, w2);       // leaky_relu(x, 0.1) in operand format
         d.seg[0].res_inv_slope = 10.f;
       } else {
-        d.seg[0].res = tens(srcR, bs, ch);
+        d.seg[0].res = tens(srcR, bs, w2);
       }
       if (j < 2) {
-        if (!rfo) d.seg[0].raw = tens(xaR, bs, ch);
-        d.seg[0].op = tens(xaO, bs, ch);
+        if (!rfo) d.seg[0].raw = tens(xaR, bs, w2);
+        d.seg[0].op = tens(xaO, bs, w2);
         d.seg[0].slope = 0.1f;
         srcR = xaR; srcO = xaO;
       } else {
         d.seg[0].beta = 1.f / 3.f;
-        if (r > 0) d.seg[0].accin = tens(sumR, bs, ch);
+        if (r > 0) d.seg[0].accin = tens(sumR, bs, w2);
         if (r < 2) {
-          d.seg[0].raw = tens(sumR, bs, ch);
+          d.seg[0].raw = tens(sumR, bs, w2);
         } else {
           d.seg[0].op = final_op;
+          d.seg[0].op.ld = final_op.ld * (w2 / ch);
           d.seg[0].slope = final_slope;
-          if (final_raw) d.seg[0].raw = tens(final_raw, bs, ch);
+          if (final_raw) d.seg[0].raw = tens(final_raw, bs, w2);
         }
       }
       QVC_PROPAGATE(run(c, d));

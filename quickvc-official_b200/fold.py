@@ -114,11 +114,28 @@ def synthesis_polyphase(updown: Tensor, w_syn: Tensor) -> Tensor:
     return e_f
 
 
+def frame_pair_filter(w: Tensor, pad_left: int) -> Tuple[Tensor, int]:
+    """(C, k, cin) dilation-1 filter -> the (2C, k', 2cin) filter of the same convolution on frame PAIRS, and its left
+    padding in pair rows (include/qvc_b200.h, qvc_model.paired):
+        out[2n + p][c] = sum_j sum_ci w[c][j][ci] x[2n + p + j - pad][ci],   2n + p + j - pad = 2 (n + a) + q
+        =>  w'[p C + c][a - a_min][q cin + ci] = w[c][2a + q - p + pad][ci]."""
+    C, k, cin = w.shape
+    a_min = (0 - pad_left) // 2
+    a_max = (1 + (k - 1) - pad_left) // 2
+    wp = torch.zeros(2 * C, a_max - a_min + 1, 2 * cin, dtype=w.dtype, device=w.device)
+    for p in (0, 1):
+        for j in range(k):
+            a, q = divmod(p + j - pad_left, 2)
+            wp[p * C:(p + 1) * C, a - a_min, q * cin:(q + 1) * cin] = w[:, j, :]
+    return wp, -a_min
+
+
 class Folded:
     """Device tensors plus the metadata `capi.Model` needs.  Keeps every tensor alive."""
 
     def __init__(self) -> None:
         self.layers: List[Dict] = []
+        self.paired: Dict[int, Dict] = {}        # layer index -> frame-paired form (frame_pair_filter)
         self.tensors: Dict[str, Tensor] = {}
 
     def add_layer(self, name: str, w: Tensor, bias, dil: int, pad_left: int, opformat: int) -> None:
@@ -134,6 +151,15 @@ class Folded:
         if bt is not None:
             self.tensors[name + ".b"] = bt
         self.layers.append(dict(name=name, w=wt, bias=bt, cin=cin, cout=cout + pad_rows, k=k, dil=dil, pad_left=pad_left))
+        # dilation-1 layers with 128 channels in and out (MRF-2): also keep the frame-paired form
+        if dil == 1 and cin == 128 and cout == 128 and k % 2 == 1 and k > 1 and bias is not None:
+            wp, pad_p = frame_pair_filter(w, pad_left)
+            wpt = to_operand(wp, opformat)
+            bpt = torch.cat([bt, bt]).contiguous()
+            self.tensors[name + ".w2"] = wpt
+            self.tensors[name + ".b2"] = bpt
+            self.paired[len(self.layers) - 1] = dict(w=wpt, bias=bpt, cin=2 * cin, cout=2 * cout, k=wp.shape[1], dil=1,
+                                                     pad_left=pad_p)
 
 
 def fold_state_dict(sd: Mapping[str, Tensor], opformat: int) -> Folded:
@@ -239,6 +265,10 @@ def build_model_struct(f: Folded, opformat: int, backend: int, chunk_utts: int) 
         m.layers[i].bias = L["bias"].data_ptr() if L["bias"] is not None else None
         m.layers[i].cin, m.layers[i].cout = L["cin"], L["cout"]
         m.layers[i].k, m.layers[i].dil, m.layers[i].pad_left = L["k"], L["dil"], L["pad_left"]
+    for i, L in f.paired.items():
+        m.paired[i].w, m.paired[i].bias = L["w"].data_ptr(), L["bias"].data_ptr()
+        m.paired[i].cin, m.paired[i].cout = L["cin"], L["cout"]
+        m.paired[i].k, m.paired[i].dil, m.paired[i].pad_left = L["k"], L["dil"], L["pad_left"]
     t = f.tensors
     m.cond_w, m.cond_b, m.cond_rows = t["cond_w"].data_ptr(), t["cond_b"].data_ptr(), COND_ROWS
     for l in range(3):

@@ -30,7 +30,7 @@ def to_op(x: torch.Tensor, opf: int) -> torch.Tensor:
 
 
 def make_args(x, w, bias, *, k, dil, pad_left, out_rows, opf, backend, epilogue=capi.EPI_LINEAR, segs=(),
-              noise=None, aux0=None, aux1=None, bias_bstride=0) -> capi.ConvArgs:
+              noise=None, aux0=None, aux1=None, bias_bstride=0, taps=None) -> capi.ConvArgs:
     """x [B][rows][cin] operand tensor, w [cout][k][cin] operand tensor; segs: list of dicts with
     col0, ncols, alpha, beta, slope, res, accin, raw, op tensors.  The caller keeps the tensors alive."""
     a = capi.ConvArgs()
@@ -49,6 +49,11 @@ def make_args(x, w, bias, *, k, dil, pad_left, out_rows, opf, backend, epilogue=
         g.res_op, g.res_inv_slope = tref(s.get("res_op")), s.get("res_inv_slope", 1.0)
     a.noise, a.aux0, a.aux1 = tref(noise), tref(aux0), tref(aux1)
     a.opformat, a.backend = opf, backend
+    if taps is not None:            # structured-zero hint: (tap_split, lo[2][2], hi[2][2])
+        a.tap_split = taps[0]
+        for p in range(2):
+            for q in range(2):
+                a.tap_lo[p][q], a.tap_hi[p][q] = taps[1][p][q], taps[2][p][q]
     return a
 
 

@@ -88,3 +88,32 @@ def test_emulated_engine_reduced_operands_within_tolerance(opf, wave_tol, stage_
     err = synth.max_abs(wave, ref["wave"])
     print(f"opformat {opf}: wave max-abs {err:.3e}, worst stage rel-L2 {worst:.3e}")
     assert err < wave_tol and worst < stage_tol
+
+
+@pytest.mark.parametrize("k", [3, 7, 11])
+def test_frame_pair_filter_is_the_same_convolution(k):
+    """include/qvc_b200.h, qvc_model.paired: the k-tap C -> C convolution on T frames equals the frame-paired filter
+    applied to the [T/2][2C] view of the same memory; exactly k + 1 of its (tap, input half) blocks are non-zero."""
+    g = torch.Generator().manual_seed(k)
+    C, T, pad = 8, 40, (k - 1) // 2
+    w = torch.randn(C, k, C, generator=g, dtype=torch.float64)
+    x = torch.randn(T, C, generator=g, dtype=torch.float64)
+    want = torch.nn.functional.conv1d(x.t()[None], w.permute(0, 2, 1), padding=pad)[0].t()
+    wp, pad_p = fold.frame_pair_filter(w, pad)
+    kp = wp.shape[1]
+    assert wp.shape == (2 * C, (k + 1) // 2 + 1, 2 * C)
+    xp = torch.nn.functional.pad(x.reshape(T // 2, 2 * C).t()[None], (pad_p, kp - 1 - pad_p))
+    got = torch.nn.functional.conv1d(xp, wp.permute(0, 2, 1))[0].t().reshape(T, C)
+    assert torch.equal(got, want) or float((got - want).abs().max()) < 1e-12
+    blocks = [(a, q) for a in range(kp) for q in (0, 1) if float(wp[:, a, q * C:(q + 1) * C].abs().sum()) > 0]
+    assert len(blocks) == k + 1
+
+
+def test_layer_table_carries_paired_forms(sd):
+    f = fold.fold_state_dict({k: v for k, v in sd.items() if not k.startswith("enc_q.")}, capi.OPF_TF32)
+    # MRF-2 = resblocks 3..5: c1.0 (dilation 1) and the three c2 layers of each; nothing else
+    names = sorted(f.layers[i]["name"] for i in f.paired)
+    want = sorted([f"dec.res.{r}.c1.0" for r in (3, 4, 5)] + [f"dec.res.{r}.c2.{j}" for r in (3, 4, 5) for j in range(3)])
+    assert names == want
+    for i, L in f.paired.items():
+        assert L["cin"] == 256 and L["cout"] == 256 and L["k"] == (f.layers[i]["k"] + 1) // 2 + 1

@@ -186,3 +186,17 @@ def test_odd_shapes_against_oracle(shape, force_pairs, sd, model_cfg, monkeypatc
         torch.cuda.synchronize()
         assert wave.shape == ref.shape
         assert synth.max_abs(wave, ref) < MODES[(precision, "tcgen05")][0], precision
+
+
+@pytest.mark.parametrize("mode", [("tf32", "tcgen05"), ("bf16", "tcgen05")], ids=["tf32", "bf16"])
+def test_frame_paired_mrf_layers_against_plain_ones(mode, sd, model_cfg, monkeypatch):
+    """QVC_FRAME_PAIR=0 runs the 128-channel MRF layers in their plain form: the same waveform up to the summation
+    order inside the dot products (which flips a few operand roundings downstream: ~1e-5 in tf32 mode, well inside the
+    1e-4 budget both forms keep against the reference goldens)."""
+    unit, mel, noise = synth.synthetic_inputs(3, 70, 1, 200, 5)
+    net = get_net(sd, model_cfg, *mode)
+    paired = net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
+    monkeypatch.setenv("QVC_FRAME_PAIR", "0")
+    plain = net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
+    err = synth.max_abs(paired, plain)
+    assert 0.0 < err < (5e-5 if mode[0] == "tf32" else 1e-3), err

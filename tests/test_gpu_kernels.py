@@ -289,3 +289,44 @@ def test_error_reporting():
     ws = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
     assert lib.qvc_spk_embed(C.byref(sw), mel.data_ptr(), 2, 200, g.data_ptr(), ws.data_ptr(), ws.numel(), stream()) == -1
     assert b"batch 1" in lib.qvc_last_error()
+
+
+@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("k,batch,rows", [(3, 2, 300), (7, 1, 1030), (11, 40, 640)], ids=["k3", "k7", "k11-pairs"])
+def test_frame_paired_convolution_with_tap_hints(opf, k, batch, rows):
+    """qvc_model.paired / qvc_conv_args.tap_split: a 128 -> 128 dilation-1 layer run as the frame-paired 256 -> 256
+    layer on the [rows/2][256] view equals the plain layer, and the structured-zero hint changes no bit."""
+    g = torch.Generator().manual_seed(k)
+    C, pad = 128, (k - 1) // 2
+    x = to_op(torch.randn(batch, rows, C, generator=g), opf).to(DEV)
+    w32 = torch.randn(C, k, C, generator=g) / (C * k) ** 0.5
+    w = to_op(w32, opf).to(DEV)
+    bias = torch.randn(C, generator=g).to(DEV)
+    res = torch.randn(batch, rows, C, generator=g).to(DEV)
+    kw = dict(opf=opf, backend=capi.BACKEND_TCGEN05)
+
+    def run(xv, wv, bv, kk, padl, nrows, width, taps=None):
+        raw = torch.full((batch, nrows, width), float("nan"), device=DEV)
+        op = torch.empty(batch, nrows, width, device=DEV, dtype=op_dtype(opf))
+        segs = [dict(col0=0, ncols=width, slope=0.1, res=res.view(batch, nrows, width), raw=raw, op=op)]
+        conv1d(xv, wv, bv, k=kk, dil=1, pad_left=padl, out_rows=nrows, segs=segs, taps=taps, **kw)
+        torch.cuda.synchronize()
+        return raw.view(batch, rows, C), op.view(batch, rows, C)
+
+    plain_raw, plain_op = run(x, w, bias, k, pad, rows, C)
+    wp32, pad_p = fold.frame_pair_filter(w.float().cpu(), pad)          # from the already rounded operands: exact
+    wp = to_op(wp32, opf).to(DEV)
+    kp = wp.shape[1]
+    lo = [[0, 0], [0, 0]]
+    hi = [[0, 0], [0, 0]]
+    for p in range(2):
+        for q in range(2):
+            nz = [a for a in range(kp) if float(wp32[p * C:(p + 1) * C, a, q * C:(q + 1) * C].abs().sum()) > 0]
+            lo[p][q], hi[p][q] = nz[0], nz[-1]
+    xp, bp = x.view(batch, rows // 2, 2 * C), torch.cat([bias, bias])
+    hint_raw, hint_op = run(xp, wp, bp, kp, pad_p, rows // 2, 2 * C, taps=(C, lo, hi))
+    full_raw, full_op = run(xp, wp, bp, kp, pad_p, rows // 2, 2 * C)
+    assert torch.equal(hint_raw, full_raw) and torch.equal(hint_op, full_op)        # skipped blocks are zeros
+    want = ref_conv(x, w, k, 1, pad, rows) + bias.double() + res.double()
+    assert float((hint_raw.double() - want).abs().max()) < _tol(opf)
+    assert float((hint_raw - plain_raw).abs().max()) < _tol(opf)                    # summation order only
