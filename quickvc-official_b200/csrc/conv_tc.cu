@@ -53,20 +53,20 @@ struct alignas(64) TcParams {
   int32_t slab_boxes, slab_box_rows;       // slab = slab_boxes TMA boxes of slab_box_rows frames
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes, w_stage_bytes;
-  // structured zeros of the filter (qvc_conv_args.tap_split): group gi's chunks lie in output half gp[gi] (2 = both),
-  // channel chunks from split_chunk on are input half 1; block (tap j) is skipped outside [jlo[p][q], jhi[p][q]]
-  // (row 2 of the tables = the union over both output halves).  Without a hint every range is [0, k-1].
-  int32_t split_chunk;
-  int32_t gp[MAXGROUPS];
-  int32_t jlo[3][2], jhi[3][2];
   int32_t debug;                           // diagnostics only (QVC_TC_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue I/O
   EpiParams ep;
+  // Structured zeros of the filter (qvc_conv_args.tap_split; only read by the TAPS = true instances, at the end of the
+  // struct so that every other launch sees the layout and code it always had): channel chunks from split_chunk on are
+  // input half q = 1; taps[h] packs, for output half h (2 = both), the tap range of input half q as nibbles: lo at
+  // bits 8q, hi at bits 8q + 4.
+  int32_t split_chunk, cout_half;
+  uint32_t taps[3];
 };
 
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
-template <int OPF, int EPI>
+template <int OPF, int EPI, bool TAPS>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ESIZE = OPF == QVC_OPF_BF16 ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;            // channels per K block
@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const int tb = rest % p.ntb, b = rest / p.ntb;
         const int t0 = tb * N;
         const int gs = p.gsize[gi];
+        uint32_t tp = 0;                           // TAPS: tap ranges of this tile's output half (union if it spans both)
+        if constexpr (TAPS) tp = p.taps[gs > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
         for (int cc = 0; cc < n_cchunks; ++cc) {
           mbar_wait(empty_slab + 8 * s, ph ^ 1u);
           if (p.debug & 1) mbar_arrive(full_slab + 8 * s);
@@ -132,8 +134,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             tma_load_3d(slab0 + s * p.slab_stage_bytes + i * p.slab_box_rows * ROW_BYTES, &p.mx, full_slab + 8 * s,
                         cc * KC, t0 - p.pad_left + i * p.slab_box_rows, b);
           if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
-          const int qh = cc >= p.split_chunk ? 1 : 0;
-          for (int j = p.jlo[p.gp[gi]][qh]; j <= p.jhi[p.gp[gi]][qh]; ++j) {
+          int jbeg = 0, jend = p.k - 1;
+          if constexpr (TAPS) {
+            const uint32_t r = cc >= p.split_chunk ? tp >> 8 : tp;
+            jbeg = (int)(r & 15u); jend = (int)((r >> 4) & 15u);
+          }
+          for (int j = jbeg; j <= jend; ++j) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
             if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
             else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
@@ -163,12 +169,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator set
       tc_fence_after();
       const uint32_t dbase = tmem_base + buf * ACC_COLS;
+      uint32_t tp = 0;
+      if constexpr (TAPS) tp = p.taps[p.gsize[gi] > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
       for (int cc = 0; cc < n_cchunks; ++cc) {
         mbar_wait(full_slab + 8 * s, ph);
         const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-        const int qh = cc >= p.split_chunk ? 1 : 0;
-        const int jfirst = p.jlo[p.gp[gi]][0], jlast = p.jhi[p.gp[gi]][qh];
-        for (int j = p.jlo[p.gp[gi]][qh]; j <= jlast; ++j) {
+        int jbeg = 0, jlast = p.k - 1, jfirst = 0;
+        if constexpr (TAPS) {
+          const uint32_t r = cc >= p.split_chunk ? tp >> 8 : tp;
+          jbeg = (int)(r & 15u); jlast = (int)((r >> 4) & 15u); jfirst = (int)(tp & 15u);
+        }
+        for (int j = jbeg; j <= jlast; ++j) {
           mbar_wait(full_w + 8 * ws, wph);
           tc_fence_after();
           const uint32_t wst = w0 + ws * p.w_stage_bytes;
@@ -353,11 +364,11 @@ bool prof_next(cudaEvent_t* e0, cudaEvent_t* e1) {
   return true;
 }
 
-template <int OPF, int EPI>
+template <int OPF, int EPI, bool TAPS>
 int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -373,7 +384,7 @@ int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = prof_next(&e0, &e1);
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e0, stream));
-  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<OPF, EPI>, p));
+  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<OPF, EPI, TAPS>, p));
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e1, stream));
   return post_launch("conv_tc_kernel");
 }
@@ -465,28 +476,6 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
       }
     }
   }
-  // structured-zero hint -> per-group tap ranges
-  p.split_chunk = 1 << 30;
-  for (int pp = 0; pp < 3; ++pp)
-    for (int q = 0; q < 2; ++q) { p.jlo[pp][q] = 0; p.jhi[pp][q] = a.k - 1; }
-  for (int gi = 0; gi < p.ngroups; ++gi) p.gp[gi] = 2;
-  if (a.tap_split > 0 && a.tap_split % kc == 0 && a.tap_split < a.cin && !paired && (a.cout / 2) % CHUNK_M == 0) {
-    p.split_chunk = a.tap_split / kc;
-    for (int q = 0; q < 2; ++q) {
-      for (int pp = 0; pp < 2; ++pp) {
-        p.jlo[pp][q] = a.tap_lo[pp][q]; p.jhi[pp][q] = a.tap_hi[pp][q];
-        QVC_REQUIRE(p.jlo[pp][q] >= 0 && p.jhi[pp][q] < a.k && p.jlo[pp][q] <= p.jhi[pp][q],
-                    "conv1d: bad tap range [%d, %d] for k = %d", p.jlo[pp][q], p.jhi[pp][q], a.k);
-      }
-      p.jlo[2][q] = p.jlo[0][q] < p.jlo[1][q] ? p.jlo[0][q] : p.jlo[1][q];
-      p.jhi[2][q] = p.jhi[0][q] > p.jhi[1][q] ? p.jhi[0][q] : p.jhi[1][q];
-    }
-    for (int gi = 0; gi < p.ngroups; ++gi) {
-      const int first_half = p.row0[gi][0] >= a.cout / 2 ? 1 : 0;
-      const int last_half = p.row0[gi][p.gsize[gi] - 1] >= a.cout / 2 ? 1 : 0;
-      p.gp[gi] = first_half == last_half ? first_half : 2;
-    }
-  }
   int ntime = (ACC_COLS / g) & ~31;
   if (rows32 < ntime) ntime = rows32;
   // Small problems (single clips, streaming chunks): a tile's K loop is a serial chain of MMAs whose cost
@@ -549,14 +538,36 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
   }
 
+  // structured-zero hint (LINEAR layers whose two output halves are whole chunks): packed tap ranges, TAPS instance
+  bool taps = false;
+  if (a.tap_split > 0 && a.tap_split % kc == 0 && a.tap_split < a.cin && !paired && (a.cout / 2) % CHUNK_M == 0 && a.k <= 16) {
+    taps = true;
+    p.split_chunk = a.tap_split / kc;
+    p.cout_half = a.cout / 2;
+    for (int h = 0; h < 3; ++h) {
+      uint32_t w = 0;
+      for (int q = 0; q < 2; ++q) {
+        int lo, hi;
+        if (h < 2) { lo = a.tap_lo[h][q]; hi = a.tap_hi[h][q]; }
+        else {
+          lo = a.tap_lo[0][q] < a.tap_lo[1][q] ? a.tap_lo[0][q] : a.tap_lo[1][q];
+          hi = a.tap_hi[0][q] > a.tap_hi[1][q] ? a.tap_hi[0][q] : a.tap_hi[1][q];
+        }
+        QVC_REQUIRE(lo >= 0 && hi < a.k && lo <= hi, "conv1d: bad tap range [%d, %d] for k = %d", lo, hi, a.k);
+        w |= ((uint32_t)lo | (uint32_t)hi << 4) << (8 * q);
+      }
+      p.taps[h] = w;
+    }
+  }
   int grid = p.ntiles < tc_sm_count() ? p.ntiles : tc_sm_count();
   const int grid_env = env_int("QVC_TC_GRID", 0);
   if (grid_env >= 1 && grid_env < grid) grid = grid_env;
 #define QVC_TC_DISPATCH(OPF)                                                                         \
   switch (a.epilogue) {                                                                              \
-    case QVC_EPI_LINEAR: return launch_variant<OPF, QVC_EPI_LINEAR>(p, grid, smem, stream);          \
-    case QVC_EPI_GATE:   return launch_variant<OPF, QVC_EPI_GATE>(p, grid, smem, stream);            \
-    default:             return launch_variant<OPF, QVC_EPI_SAMPLE>(p, grid, smem, stream);          \
+    case QVC_EPI_LINEAR: return taps ? launch_variant<OPF, QVC_EPI_LINEAR, true>(p, grid, smem, stream)    \
+                                     : launch_variant<OPF, QVC_EPI_LINEAR, false>(p, grid, smem, stream);  \
+    case QVC_EPI_GATE:   return launch_variant<OPF, QVC_EPI_GATE, false>(p, grid, smem, stream);     \
+    default:             return launch_variant<OPF, QVC_EPI_SAMPLE, false>(p, grid, smem, stream);   \
   }
   if (a.opformat == QVC_OPF_BF16) { QVC_TC_DISPATCH(QVC_OPF_BF16) }
   QVC_TC_DISPATCH(QVC_OPF_TF32)

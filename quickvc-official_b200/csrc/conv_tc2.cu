@@ -29,6 +29,11 @@ struct alignas(64) Tc2Params {
   CUtensorMap mx;                          // x as (channel, frame, utterance)
   CUtensorMap mw;                          // w as (tap*cin + channel, output channel)
   int32_t cin, k, dil, pad_left;
+  // structured zeros of the filter (qvc_conv_args.tap_split), in the same 64-byte line as the scalars around them:
+  // channel chunks from split_chunk on use taps [jlo[1], jhi[1]], the ones before it [jlo[0], jhi[0]]; without a hint
+  // both ranges are [0, k-1]
+  int32_t split_chunk;
+  int32_t jlo[2], jhi[2];
   int32_t pair_n;                          // frames per pair tile: 256 (LINEAR), 128 (GATE: two accumulators)
   int32_t nacc;                            // accumulators per CTA: 1, or 2 = (lo, hi) halves of a gate pair
   int32_t nbuf;                            // accumulator sets in TMEM: 2 (epilogue overlaps the next tile), or 1 when nacc * pair_n = 512
@@ -39,10 +44,6 @@ struct alignas(64) Tc2Params {
   int32_t slab_box_rows;                   // one TMA box per slab (128 + halo <= 256 rows)
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes;
-  // structured zeros of the filter (qvc_conv_args.tap_split): channel chunks from split_chunk on use taps
-  // [jlo[1], jhi[1]], the ones before it [jlo[0], jhi[0]]; without a hint both ranges are [0, k-1]
-  int32_t split_chunk;
-  int32_t jlo[2], jhi[2];
   EpiParams ep;
 };
 
@@ -155,6 +156,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       const uint32_t slab_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
       const uint32_t lead_full_slab = map_to_cta(full_slab, 0), lead_full_w = map_to_cta(full_w, 0);
       uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+      // tap ranges in registers: a constant-bank load per channel chunk on this single thread is on the critical path
+      const int jlo0 = p.jlo[0], jhi0 = p.jhi[0], jlo1 = p.jlo[1], jhi1 = p.jhi[1], split = p.split_chunk;
       for (int tile = pair; tile < p.ntiles; tile += npairs) {
         const int gi = tile % p.ngroups;
         const int rest = tile / p.ngroups;
@@ -166,8 +169,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           if (leader) mbar_expect_tx(full_slab + 8 * s, 2 * slab_bytes);       // bytes of both CTAs
           tma2_load_3d(slab0 + s * p.slab_stage_bytes, &p.mx, lead_full_slab + 8 * s, cc * KC, t0 - p.pad_left, b);
           if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
-          const int qh = cc >= p.split_chunk ? 1 : 0;
-          for (int j = p.jlo[qh]; j <= p.jhi[qh]; ++j) {
+          const int jbeg = cc >= split ? jlo1 : jlo0, jend = cc >= split ? jhi1 : jhi0;
+          for (int j = jbeg; j <= jend; ++j) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
             if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * w_stage_bytes);
             tma2_load_2d(w0 + ws * w_stage_bytes, &p.mw, lead_full_w + 8 * ws, j * p.cin + cc * KC, wrow);
@@ -186,6 +189,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
                              ((uint32_t)((2 * CHUNK_M) >> 4) << 24);
       const uint64_t desc_hi = smem_desc(0);
       uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
+      const int jlo0 = p.jlo[0], jhi0 = p.jhi[0], jlo1 = p.jlo[1], jhi1 = p.jhi[1], split = p.split_chunk;
       for (int tile = pair; tile < p.ntiles; tile += npairs, ++ait) {
         const uint32_t buf = p.nbuf == 2 ? (ait & 1u) : 0u;
         const uint32_t bph = p.nbuf == 2 ? ((ait >> 1) & 1u) : (ait & 1u);
@@ -195,12 +199,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         for (int cc = 0; cc < n_cchunks; ++cc) {
           mbar_wait(full_slab + 8 * s, ph);
           const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-          const int qh = cc >= p.split_chunk ? 1 : 0;
-          const int jlast = p.jhi[qh];
-          for (int j = p.jlo[qh]; j <= jlast; ++j) {
+          const int jbeg = cc >= split ? jlo1 : jlo0, jlast = cc >= split ? jhi1 : jhi0;
+          for (int j = jbeg; j <= jlast; ++j) {
             mbar_wait(full_w + 8 * ws, wph);
             tc_fence_after();
-            const uint32_t first = (cc == 0 && j == p.jlo[0]) ? 0u : 1u;
+            const uint32_t first = (cc == 0 && j == jlo0) ? 0u : 1u;
             const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
             const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * w_stage_bytes) & 0x3FFFFu) >> 4);
             if (elect_one()) {
