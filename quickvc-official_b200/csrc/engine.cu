@@ -177,13 +177,16 @@ bool residual_from_operand(const Ctx& c) {
 // One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack
 // input; on return skipO holds the operand copy of the summed skip output.
 int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, int n_layers,
-           const float* gate_bias, int64_t gate_bias_bs, int gate_bias_layer_stride) {
+           const float* gate_bias, int64_t gate_bias_bs, int gate_bias_layer_stride, int reserved_layers = 0,
+           int reserved_sms = 0) {
   const int64_t bs = (int64_t)T * HID;
   // the operand copy of x ping-pongs between two buffers: a fused layer (qvc_wn_layer) writes the new x while other
   // tiles of the same launch still read the old one as convolution halo
   const void* x_in = bf.xO;
   void* x_out = bf.xO2;
   for (int i = 0; i < n_layers; ++i) {
+    // the first `reserved_layers` layers run beside the speaker encoder and leave its SMs out of their grids
+    tc_reserve_sms(i < reserved_layers ? reserved_sms : 0);
     qvc_conv_args a = layer_args(c, l_in + i, tens(x_in, bs, HID), B, T, T);
     a.epilogue = QVC_EPI_GATE;
     if (gate_bias) { a.bias = gate_bias + (int64_t)i * gate_bias_layer_stride; a.bias_bstride = gate_bias_bs; }
@@ -485,7 +488,14 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
     a.seg[0].raw = tens(bf.xR, bs, HID);
     a.seg[0].op = tens(bf.xO, bs, HID);
     QVC_PROPAGATE(run(c, a));
-    QVC_PROPAGATE(run_wn(c, bf, B, T, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0));
+    // The encoder needs ~0.5 ms (three layers of 128 steps at ~1 us); a WN layer takes ~0.1 ms per 32000 frames of
+    // batch.  Only the layers that can overlap it give up its SMs; the rest of the stack uses the whole machine
+    // (a grid launched while the encoder still holds SMs just has its last CTAs start late).
+    const int64_t frames = (int64_t)B * T;
+    int64_t res_layers = spk_sms ? (160000 + frames - 1) / frames : 0;
+    if (res_layers > 16) res_layers = 16;
+    QVC_PROPAGATE(run_wn(c, bf, B, T, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0, (int)res_layers, spk_sms));
+    tc_reserve_sms(res_layers >= 16 ? spk_sms : 0);
     qvc_conv_args p = layer_args(c, L_ENC_PROJ, tens(bf.skipO, bs, HID), B, T, T);
     p.epilogue = QVC_EPI_SAMPLE;
     p.noise = tens(bf.noiseT, bs, HID);
