@@ -183,7 +183,10 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr: stdout carries the one JSON line
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print "NCCL version ..." on stdout; stdout carries the one
+        # JSON line, so drop that level (an explicit INFO / TRACE request is left alone, with its log sent to stderr)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = torch.device(f"cuda:{local_rank}")
