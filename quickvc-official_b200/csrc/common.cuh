@@ -2,6 +2,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -38,6 +40,15 @@ void count_launch(int n = 1);
     int _s = (expr);             \
     if (_s != QVC_OK) return _s; \
   } while (0)
+
+// Once per (kernel instance, device) set-up such as cudaFuncSetAttribute: function attributes are per device, and a
+// process may drive several (one host thread per GPU).  `flags` is the instance's own static array.
+constexpr int MAX_DEVICES = 64;
+inline bool first_use_on_device(std::atomic<bool>* flags) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return true;
+  return !flags[dev].exchange(true, std::memory_order_acq_rel);
+}
 
 inline int post_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

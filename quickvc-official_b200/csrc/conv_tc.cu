@@ -322,14 +322,15 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int sm_count() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    return v;
-  }();
-  return n;
+int sm_count() {                                  // of the current device, cached per device
+  static std::atomic<int> cache[MAX_DEVICES];
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148;
+  v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 int env_int(const char* name, int dflt) {
@@ -366,11 +367,9 @@ bool prof_next(cudaEvent_t* e0, cudaEvent_t* e1) {
 
 template <int OPF, int EPI, bool TAPS>
 int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done[MAX_DEVICES];
+  if (first_use_on_device(attr_done))
     QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-    attr_done = true;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NTHREADS);

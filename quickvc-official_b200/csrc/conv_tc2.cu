@@ -316,11 +316,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
 
 template <int OPF, int EPI>
 int launch2(const Tc2Params& p, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done[MAX_DEVICES];
+  if (first_use_on_device(attr_done))
     QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<OPF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-    attr_done = true;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NTHREADS);

@@ -341,13 +341,12 @@ extern "C" int qvc_spk_embed(const qvc_spk_weights* w, const float* mel, int bm,
 
   QVC_PROPAGATE(qvc_to_series_major(mel, mel_sm, bm, 80, tm, QVC_OPF_F32, stream_));
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set[MAX_DEVICES];
+  if (first_use_on_device(attr_set)) {
     QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
     QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
     QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
     QVC_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM));
-    attr_set = true;
   }
 
   for (int layer = 0; layer < 3; ++layer) {
