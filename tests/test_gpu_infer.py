@@ -200,3 +200,16 @@ def test_frame_paired_mrf_layers_against_plain_ones(mode, sd, model_cfg, monkeyp
     plain = net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
     err = synth.max_abs(paired, plain)
     assert 0.0 < err < (5e-5 if mode[0] == "tf32" else 1e-3), err
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process(sd, model_cfg):
+    """Function attributes, SM counts and side streams are per device: a module on cuda:1 gives cuda:0's bits."""
+    unit, mel, noise = synth.synthetic_inputs(2, 40, 1, 200, 9)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        net = SynthesizerTrn(641, 32, **model_cfg).eval()
+        net.load_state_dict(sd)
+        net = net.to(dev)
+        outs.append(net.infer(unit.to(dev), mel.to(dev), noise=noise.to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
