@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--mel-frames", type=int, default=500)
@@ -298,7 +298,7 @@ def run_ours(args, rank, local_rank, world):
     conv_flops = B * T * FLOP_PER_FRAME
     flops = conv_flops + n_windows(TM) * FLOP_PER_WINDOW
     achieved = conv_flops / (conv_ms_step * 1e-3) / 1e12
-    tf32 = args.precision != "bf16"
+    tf32 = args.precision not in ("bf16", "fp16")       # 2-byte operands run at the bf16 tensor rate
     peak = pk["bf16_sustained"] * (0.5 if tf32 else 1.0)
     peak_src = pk["source"] + ": bf16_tflops_sustained (kernels timed inside a long step)" + \
         (" x 0.5 -- TF32 operands run at half the bf16 tensor rate" if tf32 else "")
@@ -339,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"tf32": "tf32 operands, f32 accumulate/storage", "bf16": "bf16 operands, f32 accumulate",
-                  "fp32": "f32"}[args.precision],
+                  "fp16": "fp16 operands (10-bit mantissa, as TF32), f32 accumulate", "fp32": "f32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "BASELINE.json configs[1]: QuickVC SynthesizerTrn.infer, batch 64 x 10 s utterances, fp32 mode, "
                                "random-init weights, one 10 s target mel", "batch_per_gpu": B, "frames": T, "mel_frames": TM,
@@ -380,6 +380,14 @@ def run_ours(args, rank, local_rank, world):
                                  "roofline_frac_of_bf16_sustained": flops / (ms_b * 1e-3) / 1e12 / pk["bf16_sustained"],
                                  "tolerance": "waveform max-abs 2e-3, per-stage rel-L2 1.5e-2 (tests/test_gpu_infer.py)"}
             del nb
+            # fp16 operands: TF32's mantissa in two bytes -- the fp32-mode tolerance at the bf16 tensor rate
+            nh = make_net("fp16")
+            ms_h, _ = timed(lambda: nh.infer(unit, mel, noise=noise), max(3, args.steps // 2), 2)
+            line["fp16_mode"] = {"value": audio_s / (ms_h * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_h,
+                                 "roofline_frac_of_bf16_sustained": flops / (ms_h * 1e-3) / 1e12 / pk["bf16_sustained"],
+                                 "tolerance": "the fp32-mode bound: waveform max-abs 1e-4, per-stage rel-L2 1e-3 "
+                                              "(tests/test_gpu_infer.py; measured 5.9e-5 / 5.9e-4)"}
+            del nh
         # single-call latency: the 5 s clip of the metric, and BASELINE.json configs[3] (0.5 s chunks), each through
         # infer(unit, mel) as convert.py calls it and with the target-speaker embedding cached (the reference
         # recomputes it on every call, models.py:635)

@@ -46,7 +46,10 @@ typedef enum {
 typedef enum {
   QVC_OPF_F32 = 0,   /* unrounded fp32 operands; exact-fp32 FMA kernels only                  */
   QVC_OPF_TF32 = 1,  /* fp32 storage, values rounded-to-nearest to TF32 by the producer       */
-  QVC_OPF_BF16 = 2   /* bf16 storage                                                          */
+  QVC_OPF_BF16 = 2,  /* bf16 storage                                                          */
+  QVC_OPF_F16 = 3    /* IEEE half storage: the 10-bit mantissa of TF32 in 2 bytes, range +-65504 (the tensor
+                        cores run it at the bf16 rate; activations and folded filters of this model stay far
+                        inside the range, values below 6e-5 lose relative -- not absolute -- precision)    */
 } qvc_opformat;
 
 typedef enum {

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 QVC_ABI_VERSION = 4
 QVC_NUM_LAYERS = 114
 
-OPF_F32, OPF_TF32, OPF_BF16 = 0, 1, 2
+OPF_F32, OPF_TF32, OPF_BF16, OPF_F16 = 0, 1, 2, 3
 BACKEND_FMA, BACKEND_TCGEN05 = 0, 1
 EPI_LINEAR, EPI_GATE, EPI_SAMPLE = 0, 1, 2
 

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -67,8 +68,10 @@ template <int OPF> struct OpType;
 template <> struct OpType<QVC_OPF_F32>  { using type = float; };
 template <> struct OpType<QVC_OPF_TF32> { using type = float; };
 template <> struct OpType<QVC_OPF_BF16> { using type = __nv_bfloat16; };
+template <> struct OpType<QVC_OPF_F16>  { using type = __half; };
 
-inline size_t opformat_bytes(int opf) { return opf == QVC_OPF_BF16 ? 2 : 4; }
+constexpr bool opf_is16(int opf) { return opf == QVC_OPF_BF16 || opf == QVC_OPF_F16; }
+inline size_t opformat_bytes(int opf) { return opf_is16(opf) ? 2 : 4; }
 
 __device__ __forceinline__ float round_tf32(float v) {
   // round-to-nearest (ties away) to the 10-bit-mantissa TF32 grid; stays an fp32 bit pattern
@@ -84,8 +87,31 @@ template <> __device__ __forceinline__ __nv_bfloat16 to_operand<QVC_OPF_BF16>(fl
   return __float2bfloat16_rn(v);
 }
 
+// half saturates instead of overflowing to infinity: one out-of-range activation must not poison a whole utterance
+__device__ __forceinline__ float clamp_half_range(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+template <> __device__ __forceinline__ __half to_operand<QVC_OPF_F16>(float v) { return __float2half_rn(clamp_half_range(v)); }
+
 __device__ __forceinline__ float op_to_float(float v) { return v; }
 __device__ __forceinline__ float op_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float op_to_float(__half v) { return __half2float(v); }
+
+// the 16 raw bits of a 2-byte operand (zero-extended) -> float
+template <int OPF>
+__device__ __forceinline__ float op16_to_float(uint32_t bits) {
+  if constexpr (OPF == QVC_OPF_BF16) return __uint_as_float(bits << 16);
+  else return __half2float(__ushort_as_half((unsigned short)bits));
+}
+// two floats -> two 2-byte operands packed low / high
+template <int OPF>
+__device__ __forceinline__ uint32_t op16_pack2(float lo, float hi) {
+  if constexpr (OPF == QVC_OPF_BF16) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+  } else {
+    __half2 t = __floats2half2_rn(clamp_half_range(lo), clamp_half_range(hi));
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+}
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 __device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
@@ -134,28 +160,15 @@ inline TRef make_tref(const qvc_tensor& t) { return TRef{t.ptr, t.bstride, t.ld}
 // Store VEC consecutive operand values.
 template <int OPF, int VEC>
 __device__ __forceinline__ void store_operand(typename OpType<OPF>::type* dst, const float* v) {
-  if constexpr (OPF == QVC_OPF_BF16) {
+  if constexpr (opf_is16(OPF)) {
     if constexpr (VEC == 2) {
-      *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v[0], v[1]);
+      *reinterpret_cast<uint32_t*>(dst) = op16_pack2<OPF>(v[0], v[1]);
     } else if constexpr (VEC == 4) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-      __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&a);
-      u.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(dst) = u;
+      *reinterpret_cast<uint2*>(dst) = make_uint2(op16_pack2<OPF>(v[0], v[1]), op16_pack2<OPF>(v[2], v[3]));
     } else {
       static_assert(VEC == 8, "VEC");
-      uint4 u;
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-      __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-      __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
-      __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
-      u.x = *reinterpret_cast<uint32_t*>(&a);
-      u.y = *reinterpret_cast<uint32_t*>(&b);
-      u.z = *reinterpret_cast<uint32_t*>(&c);
-      u.w = *reinterpret_cast<uint32_t*>(&d);
-      *reinterpret_cast<uint4*>(dst) = u;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(op16_pack2<OPF>(v[0], v[1]), op16_pack2<OPF>(v[2], v[3]),
+                                                  op16_pack2<OPF>(v[4], v[5]), op16_pack2<OPF>(v[6], v[7]));
     }
   } else {
     float r[VEC];

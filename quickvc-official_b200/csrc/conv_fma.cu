@@ -39,6 +39,14 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, flo
   v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
 }
 
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float* v) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 template <int OPF, bool PAIRED>
 __global__ void __launch_bounds__(256) conv_fma_kernel(const FmaConvParams p) {
   using T = typename OpType<OPF>::type;
@@ -185,6 +193,7 @@ int launch_conv_fma(const qvc_conv_args& a, cudaStream_t stream) {
     case QVC_OPF_F32:  QVC_LAUNCH_FMA(QVC_OPF_F32); break;
     case QVC_OPF_TF32: QVC_LAUNCH_FMA(QVC_OPF_TF32); break;
     case QVC_OPF_BF16: QVC_LAUNCH_FMA(QVC_OPF_BF16); break;
+    case QVC_OPF_F16:  QVC_LAUNCH_FMA(QVC_OPF_F16); break;
     default: set_error("conv1d: bad opformat %d", a.opformat); return QVC_ERR_ARG;
   }
 #undef QVC_LAUNCH_FMA

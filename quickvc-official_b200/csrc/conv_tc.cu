@@ -68,9 +68,9 @@ struct alignas(64) TcParams {
 // ----------------------------------------------------------------------------------------------
 template <int OPF, int EPI, bool TAPS>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int ESIZE = OPF == QVC_OPF_BF16 ? 2 : 4;
+  constexpr int ESIZE = opf_is16(OPF) ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;            // channels per K block
-  constexpr uint32_t FMT = OPF == QVC_OPF_BF16 ? 1u : 2u;
+  constexpr uint32_t FMT = mma_format(OPF);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -516,7 +516,8 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   }
 
   // ---- tensor maps ----
-  const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (a.opformat == QVC_OPF_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.x_rows, (cuuint64_t)a.batch};
     cuuint64_t strides[2] = {(cuuint64_t)a.x.ld * esize,
@@ -569,6 +570,7 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
     default:             return launch_variant<OPF, QVC_EPI_SAMPLE, false>(p, grid, smem, stream);   \
   }
   if (a.opformat == QVC_OPF_BF16) { QVC_TC_DISPATCH(QVC_OPF_BF16) }
+  if (a.opformat == QVC_OPF_F16) { QVC_TC_DISPATCH(QVC_OPF_F16) }
   QVC_TC_DISPATCH(QVC_OPF_TF32)
 #undef QVC_TC_DISPATCH
 }

@@ -87,7 +87,7 @@ __device__ __forceinline__ void tc2_commit(uint32_t bar) {
 }
 template <int OPF>
 __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (OPF == QVC_OPF_BF16) {
+  if constexpr (opf_is16(OPF)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -104,9 +104,9 @@ __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t 
 
 template <int OPF, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
-  constexpr int ESIZE = OPF == QVC_OPF_BF16 ? 2 : 4;
+  constexpr int ESIZE = opf_is16(OPF) ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;
-  constexpr uint32_t FMT = OPF == QVC_OPF_BF16 ? 1u : 2u;
+  constexpr uint32_t FMT = mma_format(OPF);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -404,7 +404,8 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   }
   if (!fits) return QVC_ERR_UNSUPPORTED;
 
-  const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (a.opformat == QVC_OPF_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.x_rows, (cuuint64_t)a.batch};
     cuuint64_t strides[2] = {(cuuint64_t)a.x.ld * esize,
@@ -430,9 +431,11 @@ int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream) {
   if (grid_env >= 2 && grid_env / 2 < pairs) pairs = grid_env / 2;
   if (gate) {
     if (a.opformat == QVC_OPF_BF16) return launch2<QVC_OPF_BF16, QVC_EPI_GATE>(p, 2 * pairs, smem, stream);
+    if (a.opformat == QVC_OPF_F16) return launch2<QVC_OPF_F16, QVC_EPI_GATE>(p, 2 * pairs, smem, stream);
     return launch2<QVC_OPF_TF32, QVC_EPI_GATE>(p, 2 * pairs, smem, stream);
   }
   if (a.opformat == QVC_OPF_BF16) return launch2<QVC_OPF_BF16, QVC_EPI_LINEAR>(p, 2 * pairs, smem, stream);
+  if (a.opformat == QVC_OPF_F16) return launch2<QVC_OPF_F16, QVC_EPI_LINEAR>(p, 2 * pairs, smem, stream);
   return launch2<QVC_OPF_TF32, QVC_EPI_LINEAR>(p, 2 * pairs, smem, stream);
 }
 

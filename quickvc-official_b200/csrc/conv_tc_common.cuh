@@ -76,9 +76,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// operand format field of the instruction descriptor (a_format / b_format): kind::f16 takes 0 = F16, 1 = BF16;
+// kind::tf32 takes 2 = TF32
+constexpr uint32_t mma_format(int opf) { return opf == QVC_OPF_F16 ? 0u : (opf == QVC_OPF_BF16 ? 1u : 2u); }
+
 template <int OPF>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (OPF == QVC_OPF_BF16) {
+  if constexpr (opf_is16(OPF)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -96,7 +100,7 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 // Same MMA with the A operand read from TMEM (M lanes x K 32-bit columns) instead of shared memory.
 template <int OPF>
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (OPF == QVC_OPF_BF16) {
+  if constexpr (opf_is16(OPF)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
@@ -180,7 +184,7 @@ __device__ __forceinline__ void lin_load(const LinCtx& k, int t, int nv, float* 
     using OT = typename OpType<OPF>::type;
     const OT* rp = sg.res_op.at<OT>(k.b, t, k.c);
     const int ld = sg.res_op.ld;
-    if constexpr (OPF == QVC_OPF_BF16) {
+    if constexpr (opf_is16(OPF)) {
       const uint16_t* rp16 = reinterpret_cast<const uint16_t*>(rp);
       if (k.all_ok && nv == 64) {
 #pragma unroll
@@ -236,7 +240,7 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float x = rr[i];
-        if constexpr (OPF == QVC_OPF_BF16) x = __uint_as_float(__float_as_uint(x) << 16);
+        if constexpr (opf_is16(OPF)) x = op16_to_float<OPF>(__float_as_uint(x));
         rr[i] = x > 0.f ? x : x * inv;
       }
     }

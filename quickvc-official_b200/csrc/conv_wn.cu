@@ -101,7 +101,7 @@ __device__ __forceinline__ void tc2_commit(uint32_t bar) {
 }
 template <int OPF>
 __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (OPF == QVC_OPF_BF16) {
+  if constexpr (opf_is16(OPF)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -124,9 +124,9 @@ __device__ __forceinline__ void st_cluster_b16(uint32_t cluster_addr, uint16_t v
 
 template <int OPF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn_kernel(const __grid_constant__ WnParams p) {
-  constexpr int ESIZE = OPF == QVC_OPF_BF16 ? 2 : 4;
+  constexpr int ESIZE = opf_is16(OPF) ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;
-  constexpr uint32_t FMT = OPF == QVC_OPF_BF16 ? 1u : 2u;
+  constexpr uint32_t FMT = mma_format(OPF);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -318,8 +318,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
               const float a = fast_gate(lo[i] + b_lo, hi[i] + b_hi);
               const uint32_t row = (uint32_t)(blk * 32 + i);                        // row within the owner's 64 frames
               const uint32_t off = row * ROW_BYTES + ((((col_byte >> 4) ^ (row & 7u)) << 4) | (col_byte & 15u));
-              if constexpr (OPF == QVC_OPF_BF16) {
-                const __nv_bfloat16 v = __float2bfloat16_rn(a);
+              if constexpr (opf_is16(OPF)) {
+                const auto v = to_operand<OPF>(a);
                 st_cluster_b16(acts_dst + off, *reinterpret_cast<const uint16_t*>(&v));
               } else {
                 st_cluster_b32(acts_dst + off, __float_as_uint(round_tf32(a)));
@@ -460,7 +460,8 @@ extern "C" int qvc_wn_layer(const qvc_conv_args* gi, const qvc_conv_args* rs, qv
   }
   if (!fits) return QVC_ERR_UNSUPPORTED;
 
-  const CUtensorMapDataType dt = gi->opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = gi->opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (gi->opformat == QVC_OPF_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   {
     cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)gi->x_rows, (cuuint64_t)gi->batch};
     cuuint64_t strides[2] = {(cuuint64_t)gi->x.ld * esize,
@@ -492,5 +493,6 @@ extern "C" int qvc_wn_layer(const qvc_conv_args* gi, const qvc_conv_args* rs, qv
   int pairs = tc_sm_count() / 2;
   if (ntiles < pairs) pairs = ntiles;
   if (gi->opformat == QVC_OPF_BF16) return launch_wn<QVC_OPF_BF16>(p, 2 * pairs, smem, stream);
+  if (gi->opformat == QVC_OPF_F16) return launch_wn<QVC_OPF_F16>(p, 2 * pairs, smem, stream);
   return launch_wn<QVC_OPF_TF32>(p, 2 * pairs, smem, stream);
 }

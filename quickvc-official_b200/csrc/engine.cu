@@ -171,7 +171,7 @@ bool residual_from_operand(const Ctx& c) {
     return e ? atoi(e) : 1;
   }();
   if (c.m->backend != QVC_BACKEND_TCGEN05) return false;
-  return (mode >= 1 && c.m->opformat == QVC_OPF_BF16) || (mode >= 2 && c.m->opformat == QVC_OPF_TF32);
+  return (mode >= 1 && opf_is16(c.m->opformat)) || (mode >= 2 && c.m->opformat == QVC_OPF_TF32);
 }
 
 // One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack
@@ -389,7 +389,7 @@ int side_stream(SideStream** out) {
 int check_model(const qvc_model* m) {
   QVC_REQUIRE(m != nullptr, "null model");
   QVC_REQUIRE(m->abi_version == QVC_ABI_VERSION, "model built for ABI %d, library is %d", m->abi_version, QVC_ABI_VERSION);
-  QVC_REQUIRE(m->opformat >= QVC_OPF_F32 && m->opformat <= QVC_OPF_BF16, "bad opformat %d", m->opformat);
+  QVC_REQUIRE(m->opformat >= QVC_OPF_F32 && m->opformat <= QVC_OPF_F16, "bad opformat %d", m->opformat);
   QVC_REQUIRE(m->backend == QVC_BACKEND_FMA || m->backend == QVC_BACKEND_TCGEN05, "bad backend %d", m->backend);
   QVC_REQUIRE(!(m->backend == QVC_BACKEND_TCGEN05 && m->opformat == QVC_OPF_F32),
               "the tcgen05 back end needs TF32 or BF16 operands");

@@ -135,6 +135,7 @@ int to_series_major(const float* src, void* dst, int batch, int channels, int fr
     case QVC_OPF_F32:  to_series_kernel<QVC_OPF_F32><<<grid, 256, 0, st>>>(src, (float*)dst, channels, frames, live); break;
     case QVC_OPF_TF32: to_series_kernel<QVC_OPF_TF32><<<grid, 256, 0, st>>>(src, (float*)dst, channels, frames, live); break;
     case QVC_OPF_BF16: to_series_kernel<QVC_OPF_BF16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, channels, frames, live); break;
+    case QVC_OPF_F16:  to_series_kernel<QVC_OPF_F16><<<grid, 256, 0, st>>>(src, (__half*)dst, channels, frames, live); break;
     default: set_error("qvc_to_series_major: bad opformat %d", opformat); return QVC_ERR_ARG;
   }
   return post_launch("to_series_kernel");

@@ -11,7 +11,7 @@ from torch import Tensor
 
 from . import capi, fold
 
-_PRECISIONS = {"fp32": capi.OPF_F32, "tf32": capi.OPF_TF32, "bf16": capi.OPF_BF16}
+_PRECISIONS = {"fp32": capi.OPF_F32, "tf32": capi.OPF_TF32, "bf16": capi.OPF_BF16, "fp16": capi.OPF_F16}
 _BACKENDS = {"fma": capi.BACKEND_FMA, "tcgen05": capi.BACKEND_TCGEN05}
 
 TAP_SHAPES = {
@@ -47,7 +47,7 @@ class InferEngine:
         if backend not in _BACKENDS:
             raise ValueError(f"backend must be one of {sorted(_BACKENDS)}, got {backend!r}")
         if backend == "tcgen05" and precision == "fp32":
-            raise ValueError("the tcgen05 back end computes with TF32 or BF16 operands; use precision='tf32' "
+            raise ValueError("the tcgen05 back end computes with TF32, FP16 or BF16 operands; use precision='tf32' "
                              "(fp32 storage and accumulation) or backend='fma' for exact fp32")
         self.precision, self.backend = precision, backend
         self.invalidate()

@@ -64,6 +64,8 @@ def to_operand(w: Tensor, opformat: int) -> Tensor:
         return round_tf32(w)
     if opformat == capi.OPF_BF16:
         return w.to(torch.bfloat16).contiguous()
+    if opformat == capi.OPF_F16:
+        return w.to(torch.float16).contiguous()
     raise ValueError(f"bad operand format {opformat}")
 
 

@@ -221,8 +221,10 @@ class SynthesizerTrn(nn.Module):
 
     Extra, keyword-only knobs (not in the reference):
       precision  "tf32" (default; the north-star's "fp32 mode": fp32 storage and accumulation, TF32
-                 tensor-core operands), "bf16" (bf16 operands, fp32 accumulation), or "fp32" (exact
-                 fp32 CUDA-core FMA kernels, the strict mode).
+                 tensor-core operands), "fp16" (IEEE-half operands -- TF32's 10-bit mantissa in two bytes, fp32
+                 accumulation: the fp32-mode tolerance at the bf16 tensor rate, values saturate at 65504),
+                 "bf16" (bf16 operands, fp32 accumulation), or "fp32" (exact fp32 CUDA-core FMA kernels, the
+                 strict mode).
       backend    "tcgen05" or "fma"; default follows precision.
       chunk_utts decoder sub-batch size (0 = auto).
     """

@@ -25,6 +25,8 @@ def rnd(x: torch.Tensor, opf: int) -> torch.Tensor:
         return x
     if opf == capi.OPF_TF32:
         return fold.round_tf32(x.float())
+    if opf == capi.OPF_F16:
+        return x.to(torch.float16).float()
     return x.to(torch.bfloat16).float()
 
 

@@ -22,7 +22,7 @@ def tref(t: Optional[torch.Tensor], bstride=None) -> capi.Tensor:
 
 
 def op_dtype(opf: int):
-    return torch.bfloat16 if opf == capi.OPF_BF16 else torch.float32
+    return {capi.OPF_BF16: torch.bfloat16, capi.OPF_F16: torch.float16}.get(opf, torch.float32)
 
 
 def to_op(x: torch.Tensor, opf: int) -> torch.Tensor:

@@ -76,7 +76,8 @@ def test_emulated_engine_fp32_matches_oracle_and_golden(case, sd):
 
 # North-star tolerances: fp32 mode (TF32 operands, fp32 accumulate) waveform max-abs 1e-4 and
 # per-stage relative 1e-3; bf16 mode is reported with its own tolerance.
-@pytest.mark.parametrize("opf,wave_tol,stage_tol", [(capi.OPF_TF32, 1e-4, 1e-3), (capi.OPF_BF16, 2e-3, 1.5e-2)])
+@pytest.mark.parametrize("opf,wave_tol,stage_tol", [(capi.OPF_TF32, 1e-4, 1e-3), (capi.OPF_F16, 1e-4, 1e-3),
+                                                    (capi.OPF_BF16, 2e-3, 1.5e-2)])
 def test_emulated_engine_reduced_operands_within_tolerance(opf, wave_tol, stage_tol, sd):
     b, t, bm, tm = GOLDEN_CASES["small"]
     unit, mel, noise = synth.synthetic_inputs(b, t, bm, tm, 0)

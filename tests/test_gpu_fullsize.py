@@ -30,7 +30,7 @@ def big():
     return cfg, sd, unit, mel, noise
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_utterances_are_independent_at_full_size(big, precision):
     cfg, sd, unit, mel, noise = big
     net = SynthesizerTrn(641, 32, **cfg, precision=precision).eval()

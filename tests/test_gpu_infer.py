@@ -22,6 +22,9 @@ MODES = {
     ("tf32", "tcgen05"): (1e-4, 1e-3),
     ("bf16", "fma"): (2e-3, 1.5e-2),
     ("bf16", "tcgen05"): (2e-3, 1.5e-2),
+    # fp16 operands have TF32's 10-bit mantissa: the fp32-mode tolerance applies
+    ("fp16", "fma"): (1e-4, 1e-3),
+    ("fp16", "tcgen05"): (1e-4, 1e-3),
 }
 MODE_IDS = [f"{p}-{b}" for p, b in MODES]
 

@@ -15,8 +15,9 @@ DEV = "cuda:0"
 
 BACKENDS = [("fma", capi.BACKEND_FMA, capi.OPF_F32), ("fma", capi.BACKEND_FMA, capi.OPF_TF32),
             ("fma", capi.BACKEND_FMA, capi.OPF_BF16),
-            ("tc", capi.BACKEND_TCGEN05, capi.OPF_TF32), ("tc", capi.BACKEND_TCGEN05, capi.OPF_BF16)]
-IDS = ["fma-f32", "fma-tf32", "fma-bf16", "tc-tf32", "tc-bf16"]
+            ("tc", capi.BACKEND_TCGEN05, capi.OPF_TF32), ("tc", capi.BACKEND_TCGEN05, capi.OPF_BF16),
+            ("fma", capi.BACKEND_FMA, capi.OPF_F16), ("tc", capi.BACKEND_TCGEN05, capi.OPF_F16)]
+IDS = ["fma-f32", "fma-tf32", "fma-bf16", "tc-tf32", "tc-bf16", "fma-f16", "tc-f16"]
 
 
 def _tol(opf):
@@ -65,7 +66,7 @@ def test_conv_linear(geom, be):
     assert float((raw.cpu().double() - want).abs().max()) < _tol(opf) * scale
     want_op = torch.where(want > 0, want, want * 0.1)
     err_op = float((op.cpu().double() - want_op).abs().max())
-    assert err_op < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11 if opf == capi.OPF_TF32 else 0)) * scale
+    assert err_op < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11 if opf in (capi.OPF_TF32, capi.OPF_F16) else 0)) * scale
     if opf == capi.OPF_TF32:        # the operand copy must sit on the TF32 grid
         assert int((op.view(torch.int32) & 0x1FFF).abs().sum()) == 0
 
@@ -112,7 +113,7 @@ def test_conv_two_segments_wn_res_skip(be):
     assert float((skip.cpu().double() - (skip0.cpu().double() + acc[..., H:])).abs().max()) < _tol(opf) * 4
 
 
-@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16, capi.OPF_F16], ids=["tf32", "bf16", "f16"])
 @pytest.mark.parametrize("last", [False, True], ids=["res_skip", "skip_only"])
 def test_fused_wn_layer_equals_the_two_convolutions(opf, last):
     """qvc_wn_layer (one CTA-pair kernel, activations kept in shared memory) against qvc_conv1d(in_layer) +
@@ -291,7 +292,7 @@ def test_error_reporting():
     assert b"batch 1" in lib.qvc_last_error()
 
 
-@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16, capi.OPF_F16], ids=["tf32", "bf16", "f16"])
 @pytest.mark.parametrize("k,batch,rows", [(3, 2, 300), (7, 1, 1030), (11, 40, 640)], ids=["k3", "k7", "k11-pairs"])
 def test_frame_paired_convolution_with_tap_hints(opf, k, batch, rows):
     """qvc_model.paired / qvc_conv_args.tap_split: a 128 -> 128 dilation-1 layer run as the frame-paired 256 -> 256

@@ -32,7 +32,7 @@ def _ragged_inputs(B, T, lens, seed):
     return unit.to(DEV), mel.to(DEV), noise.to(DEV)
 
 
-@pytest.mark.parametrize("precision,tol", [("tf32", 0.0), ("bf16", 0.0), ("fp32", 0.0)])
+@pytest.mark.parametrize("precision,tol", [("tf32", 0.0), ("bf16", 0.0), ("fp16", 0.0), ("fp32", 0.0)])
 def test_small_ragged_batch_equals_single_calls(sd, model_cfg, precision, tol):
     net = _net(sd, model_cfg, precision)
     T = 96
