@@ -118,3 +118,26 @@ def test_layer_table_carries_paired_forms(sd):
     assert names == want
     for i, L in f.paired.items():
         assert L["cin"] == 256 and L["cout"] == 256 and L["k"] == (f.layers[i]["k"] + 1) // 2 + 1
+
+
+@pytest.mark.parametrize("opf", [capi.OPF_F32, capi.OPF_TF32], ids=["fp32", "tf32"])
+def test_emulated_ragged_batch_equals_single_utterances(opf, sd):
+    """The ragged-batch rule of the kernels (include/qvc_b200.h: operand rows at or past an utterance's length are
+    written as zero, the tail takes each utterance's own frame count) restated on the CPU emulation of the engine: every
+    utterance of a padded batch gets the waveform it gets alone, whatever its padding frames hold.  Zero operand rows are
+    exactly the zero "same" padding of the reference's convolutions (modules.py:64,133-144) -- for the polyphase
+    transposed convolutions absent input frames contribute nothing -- so nothing else about the path needs lengths."""
+    T, lens = 24, [24, 7, 16, 1]
+    B = len(lens)
+    unit, mel, noise = synth.synthetic_inputs(B, T, 1, 200, 3)
+    for b, n in enumerate(lens):                 # junk in the padding
+        unit[b, :, n:] = 37.0
+        noise[b, :, n:] = -5.0
+    emu = Emu(sd, opf)
+    wave = emu.infer(unit, mel, noise, lengths=lens)
+    assert wave.shape == (B, 1, 320 * T)
+    for b, n in enumerate(lens):
+        alone = emu.infer(unit[b:b + 1, :, :n].contiguous(), mel, noise[b:b + 1, :, :n].contiguous())
+        assert float((wave[b, 0, :320 * n] - alone[0, 0]).abs().max()) < 1e-6
+        if n < T:
+            assert float(wave[b, 0, 320 * n:].abs().max()) == 0.0
