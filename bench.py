@@ -388,6 +388,13 @@ def run_ours(args, rank, local_rank, world):
                                  "tolerance": "the fp32-mode bound: waveform max-abs 1e-4, per-stage rel-L2 1e-3 "
                                               "(tests/test_gpu_infer.py; measured 5.9e-5 / 5.9e-4)"}
             del nh
+            # strict fp32 (CUDA-core FMA back end, no operand rounding at all): the cross-check mode, for scale
+            nf = make_net("fp32")
+            ms_f, _ = timed(lambda: nf.infer(unit, mel, noise=noise), 2, 1)
+            line["fp32_strict_mode"] = {"value": audio_s / (ms_f * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_f,
+                                        "note": "exact fp32 FMA kernels (waveform max-abs 1.5e-7 vs the reference); not the "
+                                                "product path, kept to validate the tensor-core one"}
+            del nf
         # single-call latency: the 5 s clip of the metric, and BASELINE.json configs[3] (0.5 s chunks), each through
         # infer(unit, mel) as convert.py calls it and with the target-speaker embedding cached (the reference
         # recomputes it on every call, models.py:635)
