@@ -403,7 +403,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     parser.add_argument("--outdir", type=str, default="output/quickvc", help="path to output dir")
     parser.add_argument("--use_timestamp", default=False, action="store_true")
     parser.add_argument("--units-dir", type=str, default=None, help="precomputed soft units (<source stem>.pt/.npy) instead of torch.hub hubert_soft")
-    parser.add_argument("--precision", type=str, default="tf32", choices=("tf32", "bf16", "fp32"))
+    parser.add_argument("--precision", type=str, default="tf32", choices=("tf32", "fp16", "bf16", "fp32"))
     parser.add_argument("--streams", type=int, default=2, help="CUDA streams the infer calls rotate over")
     parser.add_argument("--max-batch", type=int, default=64, help="utterances per infer call")
     parser.add_argument("--no-ragged", action="store_true", help="only batch utterances of equal length and target")
