@@ -2,8 +2,9 @@
 """Benchmark of the QuickVC conversion hot path (SynthesizerTrn.infer) on B200.
 
     python bench.py --gpus N --steps K --warmup W                (our arm)
-    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port of the
-                                                                  reference's PyTorch infer, all host threads)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the reference's own PyTorch
+                                                                  infer from baseline/_ref on all host threads;
+                                                                  the oracle port when that is not staged)
 
 One "step" = one `infer` over one batch of synthetic inputs.  Workload at every N: BASELINE.json
 configs[1], batch 64 x 10 s utterances (T = 500 unit frames, one 10 s target mel), fp32 mode
@@ -29,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 FLOP_PER_FRAME = 207.2e6          # conv/linear FLOPs per unit frame per utterance
 FLOP_PER_WINDOW = 356.5e6         # speaker-encoder LSTM FLOPs per 128-frame mel window
 TAIL_BYTES_PER_POST_FRAME = 72 * 4 + 16 * 4   # read 72 fp32 channels, write 16 fp32 samples
+DECODER_FLOP_PER_UTT_10S = 89.36e9            # decoder-only conv FLOPs per 10 s utterance
 
 
 def parse():
@@ -42,7 +44,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--mel-frames", type=int, default=500)
     ap.add_argument("--chunk-utts", type=int, default=0)
-    ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds the whole run may take")
+    ap.add_argument("--cpu-baseline-budget-s", type=float, default=25.0, help="our arm: CPU seconds of the cpu_baseline leg")
+    ap.add_argument("--sweep-utts", type=int, default=4096, help="utterances of the configs[4] strong-scaling leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / latency / tail side measurements")
     return ap.parse_args()
@@ -116,23 +120,58 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm / baseline: the oracle port of the reference's infer, PyTorch fp32 on all host threads
+# CPU arm / baseline: the reference's own SynthesizerTrn.infer (baseline/_ref, staged by oracle/stage_reference.py;
+# kind "reference"), else the oracle port of it (kind "port"); PyTorch fp32 on all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_infer_rate(sd, batch, frames, mel_frames, warmup, steps):
+def cpu_infer_fn(sd, cfg):
+    """Returns (callable(unit, mel, noise) -> waveform, kind, description)."""
+    import torch
+    from oracle import qvc_oracle, stage_reference
+    if stage_reference.staged():
+        models = stage_reference.load_reference_models()
+        import contextlib
+        import warnings
+        with contextlib.redirect_stdout(sys.stderr), warnings.catch_warnings():   # the ctor prints; stdout carries the JSON line
+            warnings.simplefilter("ignore")
+            net = models.SynthesizerTrn(641, 32, **cfg).eval()
+        net.load_state_dict(sd)                  # strict: the drop-in module's state_dict IS the reference's
+
+        def run(unit, mel, noise):
+            with torch.no_grad():
+                return net.infer(unit, mel)      # the call convert.py:81 makes; it draws its own noise (models.py:94)
+        return run, "reference", "the reference's own SynthesizerTrn.infer (unmodified files staged under baseline/_ref)"
+    return (lambda unit, mel, noise: qvc_oracle.infer(sd, unit, mel, noise)), "port", \
+        "oracle port of the reference's PyTorch infer (baseline/_ref not staged)"
+
+
+def cpu_infer_rate(sd, cfg, frames, mel_frames, warmup, steps, budget_s, max_batch=64):
+    """Times `steps` calls of the CPU implementation on ONE batch size chosen up front -- the largest of 64, 32, 16, 8, 4,
+    2, 1 utterances for which warmup + steps calls fit `budget_s` seconds (probed with one 2-utterance call) -- so every
+    step of a run does the same work."""
     import torch
     import synth
-    from oracle import qvc_oracle
     torch.set_num_threads(os.cpu_count() or 1)
+    run, kind, desc = cpu_infer_fn(sd, cfg)
+    unit, mel, noise = synth.synthetic_inputs(2, frames, 1, mel_frames, 3)
+    run(unit[:1], mel, noise[:1])                                   # first-call costs (thread pool, oneDNN primitives)
+    t0 = time.perf_counter()
+    run(unit, mel, noise)
+    per_utt = (time.perf_counter() - t0) / 2
+    batch = 1
+    for b in (64, 32, 16, 8, 4, 2):
+        if b <= max_batch and (warmup + steps) * b * per_utt * 0.8 <= budget_s:   # larger batches run a little faster per utterance
+            batch = b
+            break
     unit, mel, noise = synth.synthetic_inputs(batch, frames, 1, mel_frames, 3)
     for _ in range(warmup):
-        qvc_oracle.infer(sd, unit, mel, noise)
+        run(unit, mel, noise)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        qvc_oracle.infer(sd, unit, mel, noise)
+        run(unit, mel, noise)
         times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return batch * frames / 50.0 / sec, sec
+    return batch * frames / 50.0 / sec, sec, batch, kind, desc
 
 
 def cpu_model_name():
@@ -151,20 +190,21 @@ def run_reference(args, rank):
         return
     cfg = model_cfg()
     sd = random_init_state_dict(cfg)
-    budget = max(1, args.steps + args.warmup)
-    sample = max(1, min(args.cpu_sample_batch, 240 // budget))      # ~1 s of CPU work per 16 utterances: whole run within minutes
-    rate, sec = cpu_infer_rate(sd, sample, args.frames, args.mel_frames, args.warmup, args.steps)
+    rate, sec, sample, kind, desc = cpu_infer_rate(sd, cfg, args.frames, args.mel_frames, args.warmup, args.steps,
+                                                   budget_s=args.cpu_budget_s, max_batch=args.batch)
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "audio-sec/sec", "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[1]: batch 64 x 10 s utterances, fp32; each CPU step is a bounded "
-                               f"sample of it: {sample} x {args.frames / 50:.0f} s utterances",
-                   "batch": sample, "frames": args.frames, "mel_frames": args.mel_frames},
-        "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} x {args.frames / 50:.0f} s utterances per step, oracle port of the reference's "
-                                   f"PyTorch infer, torch.set_num_threads({cores}), CPU {cpu_model_name()}"},
+        "config": {"workload": f"BASELINE.json configs[1]: QuickVC SynthesizerTrn.infer, batch 64 x 10 s utterances, fp32, "
+                               f"random-init weights, one 10 s target mel; each CPU step converts {sample} x "
+                               f"{args.frames / 50:.0f} s utterances of it" + (" (the whole batch)" if sample == args.batch else
+                                                                              f" (bounded sample: {args.cpu_budget_s:.0f} s budget)"),
+                   "batch": sample, "frames": args.frames, "mel_frames": args.mel_frames, "same_config": sample == args.batch},
+        "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} x {args.frames / 50:.0f} s utterances per step, {desc}, "
+                                   f"torch.set_num_threads({cores}), CPU {cpu_model_name()}"},
         "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,6 +214,63 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM, slice_utts=64, reps=2):
+    """configs[4]; every rank calls this.  Returns the result dict on rank 0, None elsewhere."""
+    import torch
+    from quickvc_official_b200.shard import convert_sharded, shard_range
+    n = args.sweep_utts
+    net = make_net("bf16")
+    gen = torch.Generator(device=dev).manual_seed(5)                      # the same full batch on every rank
+    unit = torch.randn(n, 256, T, device=dev, generator=gen)
+    mel = torch.randn(1, 80, TM, device=dev, generator=gen) * 2 - 5
+    lo, hi = shard_range(n, world, rank)
+    calls = [0]
+
+    def infer(u, m):                                                       # a rank's slice, 64 utterances per infer call
+        outs = []
+        for i in range(0, u.shape[0], slice_utts):
+            outs.append(net.infer(u[i:i + slice_utts], m))
+            calls[0] += 1
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
+    host = torch.empty(n, 1, 320 * T).pin_memory() if rank == 0 else None
+
+    def once():
+        out = convert_sharded(infer, unit, mel)
+        if rank == 0:
+            host.copy_(out, non_blocking=True)
+
+    convert_sharded(infer, unit[: world * slice_utts], mel)               # warm-up: folds the weights, sizes the workspace
+    once()
+    barrier()
+    per = []
+    for _ in range(reps):
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s_ev.record()
+        once()
+        e_ev.record()
+        barrier()
+        t = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per.append(float(t.item()))
+    ms = sum(per) / len(per)
+    del unit, net
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    audio_s = n * T / 50.0
+    return {"value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "scaling": "strong", "n_gpus": world, "utterances": n,
+            "ms_per_sweep": ms, "ms_min_max": [min(per), max(per)], "precision": "bf16 operands, f32 accumulate",
+            "utterances_per_gpu": hi - lo, "infer_calls_per_gpu": (hi - lo + slice_utts - 1) // slice_utts,
+            "gather_bytes_to_rank0": (n - (hi - lo)) * 320 * T * 4, "d2h_bytes_rank0": n * 320 * T * 4,
+            "note": "BASELINE.json configs[4]: shard.convert_sharded(infer, unit, mel): contiguous utterance shards, one "
+                    "infer call per 64 utterances, no hot-path collective; the torch.distributed gather of every waveform "
+                    "to rank 0 AND rank 0's copy of all of them to pinned host memory are inside the timed region "
+                    "(CUDA events, max over ranks)"}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import synth  # noqa: F401
@@ -271,6 +368,13 @@ def run_ours(args, rank, local_rank, world):
     wave_h = conv._wave_h[0]
     clocks = sampler.stop() if sampler else None
 
+    # ---- BASELINE.json configs[4]: throughput sweep, 4096 utterances x 10 s sharded over the N GPUs (STRONG scaling: the
+    # job is fixed), bf16 operands with fp32 accumulation, through quickvc_official_b200.shard.convert_sharded with the
+    # gather of all waveforms to rank 0 (and their copy to pinned host memory there) inside the timed region.
+    sweep = None
+    if args.sweep_utts > 0:
+        sweep = run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM)
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -299,19 +403,17 @@ def run_ours(args, rank, local_rank, world):
     flops = conv_flops + n_windows(TM) * FLOP_PER_WINDOW
     achieved = conv_flops / (conv_ms_step * 1e-3) / 1e12
     tf32 = args.precision not in ("bf16", "fp16")       # 2-byte operands run at the bf16 tensor rate
+    # Denominator: the driver's MEASURED_PEAKS.json, sustained figure (the kernels are timed inside a long step under
+    # the power cap); TF32 operands run at half the bf16 tensor rate.  The builder's own cuBLAS-TF32 measurement on this
+    # pool (profiles/r01_tf32_peak.json) is reported beside it as a secondary reading.
     peak = pk["bf16_sustained"] * (0.5 if tf32 else 1.0)
     peak_src = pk["source"] + ": bf16_tflops_sustained (kernels timed inside a long step)" + \
         (" x 0.5 -- TF32 operands run at half the bf16 tensor rate" if tf32 else "")
+    cublas_tf32 = None
     tf32_path = os.path.join(ROOT, "profiles", "r01_tf32_peak.json")
     if tf32 and os.path.exists(tf32_path):
-        # the TF32 denominator measured on this pool the way the driver measured the bf16 one (SURVEY.md section 8d
-        # leaves it to the builder): cuBLAS TF32 8192^3, sustained figure for kernels timed inside a long step
         with open(tf32_path) as f:
-            tp = json.load(f)
-        peak = tp["tf32_tflops_sustained"]
-        peak_src = ("measured (profiles/r01_tf32_peak.json, scripts/measure_tf32_peak.py): cuBLAS TF32 8192^3 sustained "
-                    f"{tp['tf32_tflops_sustained']:.1f} TFLOP/s (burst {tp['tf32_tflops']:.1f}); half of MEASURED_PEAKS.json's "
-                    f"bf16 sustained would be {pk['bf16_sustained'] * 0.5:.1f}")
+            cublas_tf32 = json.load(f)["tf32_tflops_sustained"]
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.precision == "tf32" and B == 64 and T == 500:
@@ -327,7 +429,8 @@ def run_ours(args, rank, local_rank, world):
         "kernel_ms_per_step": conv_ms_step, "kernel_share_of_step": conv_ms_step / ms,
         "flops_per_step": conv_flops,
         "peak_source": peak_src,
-        "frac_of_half_bf16_sustained": achieved / (pk["bf16_sustained"] * 0.5) if tf32 else None,
+        "frac_of_cublas_tf32_sustained": (achieved / cublas_tf32) if cublas_tf32 else None,
+        "cublas_tf32_sustained": cublas_tf32,
         "frac_of_bf16_sustained": achieved / pk["bf16_sustained"],
         "whole_step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / 1e12 / peak, "flops": flops},
         "note": "algorithmic FLOPs (207.2 MFLOP per unit frame per utterance, SURVEY.md section 8d) over CUDA-event launch "
@@ -356,6 +459,8 @@ def run_ours(args, rank, local_rank, world):
         "x_realtime_per_gpu": value / world,
         "step_ms_min_max": [min(per), max(per)],
     }
+    if sweep is not None:
+        line["sweep_4096_bf16"] = sweep
 
     if not args.no_extras and world == 1:
         # tail kernel alone: HBM roofline of the fused iSTFT / OLA / synthesis kernel
@@ -395,28 +500,66 @@ def run_ours(args, rank, local_rank, world):
                                         "note": "exact fp32 FMA kernels (waveform max-abs 1.5e-7 vs the reference); not the "
                                                 "product path, kept to validate the tensor-core one"}
             del nf
-        # single-call latency: the 5 s clip of the metric, and BASELINE.json configs[3] (0.5 s chunks), each through
-        # infer(unit, mel) as convert.py calls it and with the target-speaker embedding cached (the reference
-        # recomputes it on every call, models.py:635)
-        def latency(fn, n=110):
+        # ---- BASELINE.json configs[2]: the decoder alone (Multistream_iSTFT_Generator: conv_pre, ConvTranspose / MRF
+        # ResBlocks, conv_post, fused iSTFT / OLA / sub-band synthesis) at batch 256 x 10 s, through net.decode(z, g)
+        DEC_B = 256
+        dec_flops = DEC_B * DECODER_FLOP_PER_UTT_10S * (T / 500.0)
+        gz = torch.Generator(device=dev).manual_seed(9)
+        z256 = torch.randn(DEC_B, 192, T, device=dev, generator=gz)
+        g256 = torch.nn.functional.normalize(torch.randn(1, 256, device=dev, generator=gz), dim=1)
+        dec = {}
+        for prec in ("tf32", "fp16", "bf16"):
+            nd = net if prec == args.precision else make_net(prec)
+            ms_d, _ = timed(lambda: nd.decode(z256, g256), 5, 3)
+            pk_d = pk["bf16_sustained"] * (0.5 if prec == "tf32" else 1.0)
+            dec[prec] = {"value": DEC_B * T / 50.0 / (ms_d * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_d,
+                         "roofline": {"bound": "tensor", "achieved": dec_flops / (ms_d * 1e-3) / 1e12, "peak": pk_d,
+                                      "unit": "TFLOP/s", "frac": dec_flops / (ms_d * 1e-3) / 1e12 / pk_d}}
+            if nd is not net:
+                del nd
+        line["decoder_only_b256"] = {
+            "workload": f"BASELINE.json configs[2]: net.decode(z (256,192,{T}), g (1,256)) -- decoder only, 256 x 10 s",
+            "flops_per_step": dec_flops, "modes": dec,
+            "note": "whole-call CUDA-event time (L2 flushed between steps); 89.36 GFLOP per 10 s utterance (SURVEY.md section "
+                    "8d); peak = MEASURED_PEAKS.json bf16_tflops_sustained (x 0.5 for TF32 operands)"}
+        del z256
+        torch.cuda.empty_cache()
+
+        # ---- single-call latency: the 5 s clip of the metric, and BASELINE.json configs[3] (0.5 s chunks, batch 1) in the
+        # fp32 mode (tf32), fp16 and bf16: p50 / p99 over 1000 calls each, through infer(unit, mel) as convert.py calls it
+        # and with the target-speaker embedding cached (the reference recomputes it on every call, models.py:635)
+        def latency(fn, n=1000, skip=20):
             lat = []
-            for i in range(n):
+            for i in range(n + skip):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 fn()
                 e.record()
                 torch.cuda.synchronize()
-                if i >= 10:
+                if i >= skip:
                     lat.append(s.elapsed_time(e))
             lat.sort()
-            return {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))]}
+            return {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "calls": len(lat)}
 
+        from quickvc_official_b200.pipeline import GraphedInfer
         m5 = mel[:, :, :250].contiguous()
-        emb = net.embed_speaker(m5)
         for name, frames in (("latency_5s_clip_ms", 250), ("latency_0p5s_chunk_ms", 25)):
             u1, n1 = unit[:1, :, :frames].contiguous(), noise[:1, :, :frames].contiguous()
-            line[name] = latency(lambda: net.infer(u1, m5, noise=n1))
-            line[name]["cached_speaker"] = latency(lambda: net.infer_with_embedding(u1, emb, noise=n1))
+            entry = {}
+            for prec in ("tf32", "fp16", "bf16"):
+                nl = net if prec == args.precision else make_net(prec)
+                emb = nl.embed_speaker(m5)
+                r = latency(lambda: nl.infer(u1, m5, noise=n1))
+                r["cached_speaker"] = latency(lambda: nl.infer_with_embedding(u1, emb, noise=n1))
+                gi = GraphedInfer(nl, 1, frames, mel_frames=0, device=dev)
+                gi(u1, emb, n1)
+                r["cached_speaker_cuda_graph"] = latency(lambda: gi(u1, emb, n1))
+                entry[prec] = r
+                del gi
+                if nl is not net:
+                    del nl
+            entry.update(entry[args.precision if args.precision in entry else "tf32"])      # top-level p50 / p99: this run's mode
+            line[name] = entry
 
         # SURVEY.md section 8f "next" #3: ragged batches -- the same B utterances with lengths drawn from 5 .. 10 s, sorted
         # as the conversion driver does, padded to the longest; the rate counts live audio only
@@ -451,11 +594,10 @@ def run_ours(args, rank, local_rank, world):
 
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        sample = max(1, args.cpu_sample_batch)
-        rate, sec = cpu_infer_rate(sd, sample, T, TM, 1, 8)
-        line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} x {T / 50:.0f} s utterances, oracle port of the reference's PyTorch infer "
-                                          f"(fp32, torch.set_num_threads({cores})), 1 warm-up + 8 timed calls of {sec:.2f} s, "
+        rate, sec, sample, kind, desc = cpu_infer_rate(sd, cfg, T, TM, 1, 3, budget_s=args.cpu_baseline_budget_s, max_batch=B)
+        line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                                "sample": f"{sample} x {T / 50:.0f} s utterances per call, {desc} (fp32, "
+                                          f"torch.set_num_threads({cores})), 1 warm-up + 3 timed calls of {sec:.2f} s, "
                                           f"CPU {cpu_model_name()}"}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -66,12 +66,14 @@ def get_hparams_from_file(config_path: str) -> HParams:
         return HParams(**json.load(f))
 
 
-def load_checkpoint(checkpoint_path: str, model: torch.nn.Module) -> int:
+def load_checkpoint(checkpoint_path: str, model: torch.nn.Module, trust: bool = False) -> int:
     """utils.py:148-178 without the optimizer: key-wise load of `checkpoint['model']`, keys missing from the file keep
-    the module's values; returns the stored iteration."""
+    the module's values; returns the stored iteration.  The reference checkpoint holds tensors, optimizer state and
+    scalars only, so it is unpickled with `weights_only=True`; `trust` (CLI: --trust-checkpoint) allows arbitrary
+    pickled objects for files from a source the caller vouches for."""
     if not os.path.isfile(checkpoint_path):
         raise FileNotFoundError(checkpoint_path)
-    ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=not trust)
     saved = ckpt["model"]
     state = model.state_dict()
     model.load_state_dict({k: saved.get(k, v) for k, v in state.items()})
@@ -179,7 +181,7 @@ class UnitsDirectory:
         for ext in (".pt", ".npy"):
             p = os.path.join(self.directory, stem + ext)
             if os.path.isfile(p):
-                u = torch.load(p, map_location="cpu") if ext == ".pt" else torch.from_numpy(np.load(p))
+                u = torch.load(p, map_location="cpu", weights_only=True) if ext == ".pt" else torch.from_numpy(np.load(p))
                 u = u.to(torch.float32)
                 if u.dim() == 2:
                     u = u.unsqueeze(0)
@@ -383,7 +385,8 @@ class Converter:
         return written
 
 
-def build_net(hps: HParams, ptfile: Optional[str], device: torch.device, precision: str = "tf32"):
+def build_net(hps: HParams, ptfile: Optional[str], device: torch.device, precision: str = "tf32",
+              trust_checkpoint: bool = False):
     """convert.py:35-41."""
     from .models import SynthesizerTrn
 
@@ -391,7 +394,7 @@ def build_net(hps: HParams, ptfile: Optional[str], device: torch.device, precisi
                          precision=precision, **hps.model.as_dict()).to(device)
     net.eval()
     if ptfile is not None:
-        load_checkpoint(ptfile, net)
+        load_checkpoint(ptfile, net, trust=trust_checkpoint)
     return net
 
 
@@ -408,6 +411,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     parser.add_argument("--max-batch", type=int, default=64, help="utterances per infer call")
     parser.add_argument("--no-ragged", action="store_true", help="only batch utterances of equal length and target")
     parser.add_argument("--seed", type=int, default=None, help="seed of the prior's noise draw (default: unseeded, as the reference)")
+    parser.add_argument("--trust-checkpoint", action="store_true",
+                        help="unpickle --ptfile without weights_only (it may then run arbitrary code: trusted files only)")
     args = parser.parse_args(argv)
 
     # one process per GPU under torchrun: rank r converts lines r, r + world, ... on GPU LOCAL_RANK
@@ -417,7 +422,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     device = torch.device("cuda", torch.cuda.current_device())
     hps = get_hparams_from_file(args.hpfile)
     print("Loading model...")
-    net = build_net(hps, args.ptfile, device, args.precision)
+    net = build_net(hps, args.ptfile, device, args.precision, args.trust_checkpoint)
     print("Number of parameter: %.2fM" % (sum(p.nelement() for p in net.parameters()) / 1e6))
     encoder = None if args.units_dir else load_hubert_soft(device)
     conv = Converter(net, hps, content_encoder=encoder, units_dir=args.units_dir, streams=args.streams,

@@ -185,8 +185,9 @@ extern "C" int qvc_check_device(int dev) {
   QVC_REQUIRE(dev >= 0 && dev < n, "device %d out of range (%d devices)", dev, n);
   cudaDeviceProp pr;
   QVC_CHECK_CUDA(cudaGetDeviceProperties(&pr, dev));
-  if (pr.major != 10) {
-    set_error("device %d is sm_%d%d; libqvc_b200 only carries sm_100a code", dev, pr.major, pr.minor);
+  // the library holds sm_100a SASS only and no PTX: arch-specific ("a") code does not run on any other part, sm_103 included
+  if (pr.major != 10 || pr.minor != 0) {
+    set_error("device %d is sm_%d%d; libqvc_b200 only carries sm_100a code (B200)", dev, pr.major, pr.minor);
     return QVC_ERR_NO_DEVICE;
   }
   return QVC_OK;

@@ -35,6 +35,8 @@ class InferEngine:
         self._model: Optional[capi.Model] = None
         self._device: Optional[torch.device] = None
         self._ws: Dict[Tuple[torch.device, int], Tensor] = {}     # one workspace per (device, stream)
+        self._watch: list = []                                    # tensors the folded copies were made from
+        self._versions = -1
         self.chunk_utts = int(chunk_utts)
         self.configure(precision, backend)
 
@@ -55,6 +57,13 @@ class InferEngine:
     def invalidate(self) -> None:
         self._folded = None
         self._model = None
+        self._watch = []
+        self._versions = -1
+
+    def _param_versions(self) -> int:
+        # in-place edits (p.data.copy_, optimiser steps, manual remove-weight-norm) bump a tensor's version
+        # counter; their sum is a cheap fingerprint of "the weights the fold was made from are still the weights"
+        return sum(t._version for t in self._watch)
 
     # ------------------------------------------------------------------ folded weights
     def _ensure_model(self, device: torch.device) -> capi.Model:
@@ -62,6 +71,8 @@ class InferEngine:
             raise capi.QvcError("SynthesizerTrn.infer runs on a B200 only: move the module and its inputs to "
                                 "a CUDA device (there is no CPU path)")
         lib = capi.load()
+        if self._model is not None and self._device == device and self._param_versions() != self._versions:
+            self.invalidate()                      # a parameter was edited in place since the fold
         if self._model is None or self._device != device:
             capi.check(lib.qvc_check_device(device.index if device.index is not None else torch.cuda.current_device()),
                        "qvc_check_device")
@@ -70,7 +81,13 @@ class InferEngine:
                 if v.device != device:
                     raise capi.QvcError(f"parameter {k} lives on {v.device}, inputs on {device}")
             opf = _PRECISIONS[self.precision]
-            self._folded = fold.fold_state_dict(sd, opf)
+            # The fold is host arithmetic (fp64, once per load): the device only ever runs this library's own kernels.
+            # The folded tensors are then uploaded on the current stream and that stream is synchronised once, so any
+            # other stream may use the model struct afterwards without an ordering of its own.
+            self._watch = list(sd.values())
+            self._versions = self._param_versions()
+            self._folded = fold.fold_state_dict({k: v.detach().cpu() for k, v in sd.items()}, opf).to(device)
+            torch.cuda.current_stream(device).synchronize()
             self._model = fold.build_model_struct(self._folded, opf, _BACKENDS[self.backend], self.chunk_utts)
             self._device = device
         return self._model

@@ -140,6 +140,24 @@ class Folded:
         self.paired: Dict[int, Dict] = {}        # layer index -> frame-paired form (frame_pair_filter)
         self.tensors: Dict[str, Tensor] = {}
 
+    def to(self, device) -> "Folded":
+        """Move every device-side tensor (the `*_host` copies stay on the host); the layer tables follow."""
+        moved: Dict[int, Tensor] = {}
+
+        def mv(t):
+            if t is None:
+                return None
+            if id(t) not in moved:
+                moved[id(t)] = t.to(device)
+            return moved[id(t)]
+
+        for name in list(self.tensors):
+            if not name.endswith("_host"):
+                self.tensors[name] = mv(self.tensors[name])
+        for L in list(self.layers) + list(self.paired.values()):
+            L["w"], L["bias"] = mv(L["w"]), mv(L["bias"])
+        return self
+
     def add_layer(self, name: str, w: Tensor, bias, dil: int, pad_left: int, opformat: int) -> None:
         cout, k, cin = w.shape
         pad_rows = (-cout) % 16

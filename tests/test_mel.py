@@ -86,3 +86,60 @@ def test_mel_feeds_infer_like_convert_py(sd, model_cfg):
     wave = net.infer(unit.to("cuda:0"), mel, noise=noise.to("cuda:0"))
     ref = qvc_oracle.infer(sd, unit, mel_oracle.wave_to_mel(wav_tgt, *ARGS), noise)
     assert float((wave.cpu() - ref).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# Pin to the reference itself: tests/golden/mel_*.npz are outputs of the UNMODIFIED /root/reference/mel_processing.py
+# (tests/golden/make_mel_golden.py: the module imported as is, only the absent `librosa.filters.mel` stubbed with
+# torchaudio's librosa-compatible Slaney bank).
+# ------------------------------------------------------------------------------------------------
+def _mel_golden(name):
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_mel_golden
+    batch, samples, seed = make_mel_golden.CASES[name]
+    with np.load(os.path.join(GOLDEN, f"mel_{name}.npz")) as z:
+        return make_mel_golden.waves(batch, samples, seed), torch.from_numpy(z["mel"])
+
+
+MEL_CASES = ("10s", "1s_b3", "ragged", "min")
+
+
+@pytest.mark.parametrize("name", MEL_CASES)
+def test_oracle_matches_reference_mel_golden(name):
+    y, gold = _mel_golden(name)
+    got = mel_oracle.wave_to_mel(y, *ARGS)
+    assert got.shape == gold.shape
+    # same torch calls on the same machine class; the only independent piece is the restated filterbank
+    assert float((got - gold).abs().max()) < 2e-5, float((got - gold).abs().max())
+
+
+def test_oracle_matches_live_reference_mel():
+    import os
+    import sys
+    from conftest import GOLDEN, REFERENCE
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("reference tree not mounted")
+    pytest.importorskip("torchaudio")
+    sys.path.insert(0, GOLDEN)
+    import make_mel_golden
+    make_mel_golden.stub_librosa()
+    sys.path.insert(0, REFERENCE)
+    import mel_processing
+    y = make_mel_golden.waves(2, 20000, 11)
+    want = mel_processing.wave_to_mel(y, *ARGS)
+    got = mel_oracle.wave_to_mel(y, *ARGS)
+    assert float((got - want).abs().max()) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", MEL_CASES)
+def test_wave_to_mel_matches_reference_golden_on_b200(name):
+    y, gold = _mel_golden(name)
+    got = qmel.wave_to_mel(y.to("cuda:0"), *ARGS)
+    torch.cuda.synchronize()
+    assert got.shape == gold.shape and got.dtype == torch.float32
+    # fp32 GEMM of 1280 terms in a different summation order than torch.stft's FFT, then a log
+    assert float((got.cpu() - gold).abs().max()) < 3e-4, float((got.cpu() - gold).abs().max())
