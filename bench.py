@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--chunk-utts", type=int, default=0)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds the whole run may take")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=25.0, help="our arm: CPU seconds of the cpu_baseline leg")
+    ap.add_argument("--e2e-reps", type=int, default=3, help="timed end-to-end regions of --steps steps each (median reported)")
     ap.add_argument("--sweep-utts", type=int, default=4096, help="utterances of the configs[4] strong-scaling leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / latency / tail side measurements")
@@ -88,22 +89,61 @@ def random_init_state_dict(cfg):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled every 100 ms DURING the timed regions.  Reads NVML in-process (the library
+    nvidia-smi itself reads; `nvidia_ml_py`): spawning an nvidia-smi process every 200 ms was measured to stall the
+    launching thread for tens of milliseconds on some boxes -- a 5-step end-to-end region once read 2x too slow.  Falls
+    back to nvidia-smi when NVML cannot be loaded."""
+
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML enumerates all of them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        try:
+            power = n.nvmlDeviceGetPowerUsage(self._handle) / 1000.0
+        except Exception:
+            power = 0.0
+        flags = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        return [str(sm), str(mx), f"{power:.1f}"] + ["Active" if reasons & flags[k] else "Not Active"
+                                                      for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.1 if self._nvml is not None else 0.5)
 
     def stop(self):
         self._stop_evt.set()
@@ -116,7 +156,9 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(self.rows))
+        pw = max((float(r[2]) for r in self.rows if len(r) > 2), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(self.rows),
+                    power_w_max=pw, source="nvml" if self._nvml is not None else "nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +372,7 @@ def run_ours(args, rank, local_rank, world):
         return float(tot.item()) / steps, per
 
     audio_s = B * T / 50.0
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("QVC_BENCH_NO_SAMPLER") else None
     if sampler:
         sampler.start()
 
@@ -354,16 +396,19 @@ def run_ours(args, rank, local_rank, world):
         conv.drain()
 
     e2e_run(args.warmup)
-    barrier()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    e2e_run(args.steps)
-    e_ev.record()
-    barrier()
-    tot = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    ms_e2e = float(tot.item()) / args.steps
+    e2e_all = []
+    for _ in range(max(1, args.e2e_reps)):          # the region is repeated; the MEDIAN region is reported (all are listed)
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        e2e_run(args.steps)
+        e_ev.record()
+        barrier()
+        tot = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        e2e_all.append(float(tot.item()) / args.steps)
+    ms_e2e = sorted(e2e_all)[len(e2e_all) // 2]
     e2e_value = world * audio_s / (ms_e2e * 1e-3)
     wave_h = conv._wave_h[0]
     clocks = sampler.stop() if sampler else None
@@ -449,7 +494,7 @@ def run_ours(args, rank, local_rank, world):
                    "precision": args.precision, "l2": "flushed (256 MB memset) between timed steps",
                    "audio_seconds_per_step_per_gpu": audio_s},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e,
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e, "ms_per_step_regions": e2e_all,
                 "h2d_bytes_per_step": unit_h.numel() * 4 + mel_h.numel() * 4, "d2h_bytes_per_step": wave_h.numel() * 4,
                 "api": "quickvc_official_b200.pipeline.PipelinedConverter.submit(unit_host, mel_host) -> net.infer(unit, mel); "
                        "pinned host buffers, H2D / kernels / D2H of consecutive steps overlapped on three streams"},

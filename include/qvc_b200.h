@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QVC_ABI_VERSION 4
+#define QVC_ABI_VERSION 5
 
 typedef struct CUstream_st* qvc_stream_t;   /* == cudaStream_t */
 
@@ -136,6 +136,19 @@ typedef struct {
 } qvc_conv_args;
 
 int qvc_conv1d(const qvc_conv_args* args, qvc_stream_t stream);
+
+/* Sum of series convolutions with ONE fused epilogue (tcgen05 back end): the accumulator collects
+ *     acc[b][t][n] = sum_{i < nsrc} conv(srcs[i]->x, srcs[i]->w)[b][t][n]        (each source with its own k, dil, pad_left, taps)
+ * in source order inside tensor memory, then the QVC_EPI_LINEAR epilogue of srcs[0] (one segment, no accin) runs with
+ *     bias = sum_i srcs[i]->bias,   residual = sum_i srcs[i]->seg[0].res (or .res_op, undone with that source's res_inv_slope):
+ *     v = beta * (alpha * (acc + bias) + res_0 + res_1 + ...);  raw <- v;  op <- round(leaky_relu(v, slope)).
+ * This is the mean of the three ResBlocks of an MRF stage (models.py:378-384) taken where their last convolutions
+ * (modules.py:153-154) accumulate: xs / 3 = (1/3) sum_r (x_r + c2_r(t_r)) -- the fp32 running sum never exists in memory.
+ * All sources share batch, x_rows == out_rows, cin, cout, opformat and backend; 1 <= nsrc <= QVC_MAX_SUM_SOURCES.
+ * Returns QVC_ERR_UNSUPPORTED (error string untouched) for the FMA back end: the caller then chains qvc_conv1d calls
+ * through `accin`. */
+#define QVC_MAX_SUM_SOURCES 3
+int qvc_conv1d_sum(const qvc_conv_args* const* srcs, int nsrc, qvc_stream_t stream);
 
 /* One whole WN layer (modules.py:88-112) in one launch: `in_layer` (QVC_EPI_GATE) followed by `res_skip`
  * (QVC_EPI_LINEAR, k = 1) whose input is the gate output.  Equivalent to qvc_conv1d(in_layer) then
@@ -263,6 +276,33 @@ typedef struct {
   qvc_spk_weights spk;
   qvc_tail_weights tail;
 } qvc_model;
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight preparation: reference-layout state_dict -> qvc_model, once per load (replaces what the reference recomputes
+ * on every forward: weight_norm at every weight_norm(...) site, Flip, cond_layer(g), ConvTranspose1d, the zero-stuffing
+ * + synthesis filter -- see csrc/fold.cu).  Host arithmetic in double precision; the device receives one copy.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const char*  name;     /* key of the reference's state_dict (models.py:551-591; utils.py:161-176), e.g.
+                            "dec.resblocks.3.convs1.0.weight_v"; enc_q.* entries may be present and are ignored */
+  const float* data;     /* HOST pointer, fp32, contiguous, in the reference's (PyTorch) element order */
+  int64_t      numel;
+} qvc_state_entry;
+
+/* bytes of the block qvc_prepare_weights / qvc_fold_host fill for `opformat` (0 = bad format) */
+size_t qvc_prepared_bytes(int opformat);
+/* Folds the entries into `device_block` (device memory of >= qvc_prepared_bytes(opformat), owned by the caller and kept
+ * alive as long as `model` is used) and fills *model with pointers into it.  `tail_host` (optional): 16 + 272 host
+ * floats, owned by the caller for the same lifetime, that receive the host copies of the tail coefficients
+ * (qvc_tail_weights.window_host / synth_host).  The copy is enqueued on `stream`, which is synchronised before
+ * returning.  A missing key or a wrong element count fails with QVC_ERR_ARG naming the key. */
+int qvc_prepare_weights(const qvc_state_entry* entries, int n_entries, int opformat, int backend,
+                        void* device_block, size_t device_bytes, float* tail_host, qvc_model* model,
+                        qvc_stream_t stream);
+/* The same fold into HOST memory (pointers in *model then refer to `block`): what the tests compare with the Python
+ * statement of the fold (quickvc-official_b200/fold.py); no device needed. */
+int qvc_fold_host(const qvc_state_entry* entries, int n_entries, int opformat, int backend, void* block,
+                  size_t block_bytes, float* tail_host, qvc_model* model);
 
 /* Optional per-stage copies in the reference layout (B, C, T) fp32; NULL = skip.
  * Names follow SURVEY.md section 8a. */

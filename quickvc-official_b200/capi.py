@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libqvc_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-QVC_ABI_VERSION = 4
+QVC_ABI_VERSION = 5
 QVC_NUM_LAYERS = 114
 
 OPF_F32, OPF_TF32, OPF_BF16, OPF_F16 = 0, 1, 2, 3
@@ -76,6 +76,10 @@ class Model(C.Structure):
                 ("spk", SpkWeights), ("tail", TailWeights)]
 
 
+class StateEntry(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
+
+
 class Taps(C.Structure):
     _fields_ = [("g", C.c_void_p), ("m_p", C.c_void_p), ("logs_p", C.c_void_p), ("z_p", C.c_void_p),
                 ("flow", C.c_void_p * 4), ("conv_pre", C.c_void_p), ("ups0", C.c_void_p),
@@ -86,6 +90,7 @@ class Taps(C.Structure):
 # every symbol include/qvc_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qvc_conv1d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "qvc_conv1d_sum": (C.c_int, [C.POINTER(C.POINTER(ConvArgs)), C.c_int, C.c_void_p]),
     "qvc_wn_layer": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(ConvArgs), C.c_void_p]),
     "qvc_to_series_major": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "qvc_from_series_major": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -103,6 +108,11 @@ SYMBOLS = {
                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),
     "qvc_decode": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                              C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qvc_prepared_bytes": (C.c_size_t, [C.c_int]),
+    "qvc_prepare_weights": (C.c_int, [C.POINTER(StateEntry), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.POINTER(Model), C.c_void_p]),
+    "qvc_fold_host": (C.c_int, [C.POINTER(StateEntry), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                C.POINTER(Model)]),
     "qvc_last_error": (C.c_char_p, []),
     "qvc_abi_version": (C.c_int, []),
     "qvc_launch_count": (C.c_uint64, []),
@@ -132,6 +142,23 @@ def load() -> C.CDLL:
         raise QvcError(f"{LIB_NAME} has ABI {lib.qvc_abi_version()}, binding expects {QVC_ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def state_entries(sd):
+    """state_dict (CPU tensors) -> (array of qvc_state_entry, keep-alive list): fp32, contiguous, enc_q.* left out."""
+    import torch
+    keep, rows = [], []
+    for k, v in sd.items():
+        if k.startswith("enc_q."):
+            continue
+        t = v.detach().to("cpu", torch.float32).contiguous()
+        name = k.encode()
+        keep.append((t, name))
+        rows.append((name, t.data_ptr(), t.numel()))
+    arr = (StateEntry * len(rows))()
+    for i, (name, ptr, n) in enumerate(rows):
+        arr[i].name, arr[i].data, arr[i].numel = name, ptr, n
+    return arr, keep
 
 
 def check(status: int, what: str) -> None:

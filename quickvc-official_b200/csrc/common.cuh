@@ -148,11 +148,37 @@ struct EpiParams {
   TRef noise, aux0, aux1;
   const int32_t* live;  // ragged batches: utterance b has live[b] * live_mul live rows (nullptr: all of them)
   int32_t live_mul;
+  // sum of convolutions (qvc_conv1d_sum): residuals / biases of sources 1 and 2 (source 0 is seg[0] / bias)
+  int32_t nsum;         // number of sources (1 = an ordinary convolution)
+  TRef xres[2], xres_op[2];
+  float xres_inv_slope[2];
+  const float* xbias[2];
 };
 
 // rows of utterance b whose operand outputs are real; the rest are written as zero (qvc_conv_args.live_units)
 __device__ __forceinline__ int live_rows(const EpiParams& ep, int b) {
   return ep.live ? ep.live[b] * ep.live_mul : 0x7fffffff;
+}
+
+// Ragged batches: a tile whose first row lies DEAD_MARGIN rows or more past its utterance's own end is skipped by all
+// warp roles of the tensor-core kernels.  The margin keeps the zero rows a later layer reads as halo past the end
+// (at most (k - 1) * dil / 2 = 25 rows on this path) written; rows beyond it are never read by a live tile's live columns.
+// `live_s` is the kernel's shared-memory copy of ep.live[0 .. LIVE_CACHE) (load_live_cache): the single-thread TMA / MMA
+// roles would otherwise pay a dependent global load per tile, dead or not.
+constexpr int DEAD_MARGIN = 32;
+constexpr int LIVE_CACHE = 2048;
+inline size_t live_cache_bytes(const qvc_conv_args& a) {
+  return a.live_units ? 4u * (size_t)(a.batch < LIVE_CACHE ? a.batch : LIVE_CACHE) : 0u;
+}
+__device__ __forceinline__ void load_live_cache(const EpiParams& ep, int batch, int32_t* live_s) {   // all threads of the CTA
+  if (ep.live == nullptr) return;
+  const int n = batch < LIVE_CACHE ? batch : LIVE_CACHE;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) live_s[i] = ep.live[i];
+}
+__device__ __forceinline__ bool tile_dead(const EpiParams& ep, const int32_t* live_s, int b, int t0) {
+  if (ep.live == nullptr) return false;
+  const int lv = b < LIVE_CACHE ? live_s[b] : ep.live[b];
+  return t0 >= lv * ep.live_mul + DEAD_MARGIN;
 }
 
 inline TRef make_tref(const qvc_tensor& t) { return TRef{t.ptr, t.bstride, t.ld}; }
@@ -314,9 +340,12 @@ __device__ __forceinline__ void epi_sample(const EpiParams& ep, int b, int t, in
 
 // host-side translation of the public argument struct
 int build_epi_params(const qvc_conv_args& a, EpiParams* ep);
+int add_sum_sources(const qvc_conv_args* const* srcs, int nsrc, EpiParams* ep);
 
 // kernels' host launchers (defined in the respective .cu files)
 int launch_conv_fma(const qvc_conv_args& a, cudaStream_t stream);
 int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream);
+// sum of nsrc convolutions (qvc_conv1d_sum); srcs[0] carries the epilogue
+int launch_conv_tc_sum(const qvc_conv_args* const* srcs, int nsrc, cudaStream_t stream);
 
 }  // namespace qvc

@@ -141,6 +141,13 @@ int build_epi_params(const qvc_conv_args& a, EpiParams* ep) {
   ep->bias_bs = a.bias_bstride;
   ep->live = a.live_units;
   ep->live_mul = a.live_mul;
+  ep->nsum = 1;
+  for (int i = 0; i < 2; ++i) {
+    ep->xres[i] = TRef{nullptr, 0, 0};
+    ep->xres_op[i] = TRef{nullptr, 0, 0};
+    ep->xres_inv_slope[i] = 1.f;
+    ep->xbias[i] = nullptr;
+  }
   QVC_REQUIRE(!a.live_units || a.live_mul >= 1, "conv1d: live_units needs live_mul >= 1 (got %d)", a.live_mul);
   QVC_REQUIRE(a.epilogue >= QVC_EPI_LINEAR && a.epilogue <= QVC_EPI_SAMPLE, "conv1d: bad epilogue %d", a.epilogue);
   if (a.epilogue == QVC_EPI_LINEAR) {
@@ -170,6 +177,35 @@ int build_epi_params(const qvc_conv_args& a, EpiParams* ep) {
   ep->aux0 = make_tref(a.aux0);
   ep->aux1 = make_tref(a.aux1);
   if (a.epilogue == QVC_EPI_SAMPLE) QVC_REQUIRE(a.noise.ptr != nullptr, "conv1d: SAMPLE epilogue needs noise");
+  return QVC_OK;
+}
+
+// qvc_conv1d_sum: the residuals and biases of sources 1.. join the epilogue description of source 0
+int add_sum_sources(const qvc_conv_args* const* srcs, int nsrc, EpiParams* ep) {
+  const qvc_conv_args& a0 = *srcs[0];
+  QVC_REQUIRE(a0.epilogue == QVC_EPI_LINEAR && a0.nseg == 1 && !a0.seg[0].accin.ptr,
+              "conv1d_sum: source 0 must carry a one-segment LINEAR epilogue without accin");
+  QVC_REQUIRE(a0.seg[0].col0 == 0 && a0.seg[0].ncols == a0.cout, "conv1d_sum: the segment must span all %d columns", a0.cout);
+  const bool from_op = a0.seg[0].res_op.ptr != nullptr;
+  ep->nsum = nsrc;
+  for (int i = 1; i < nsrc; ++i) {
+    const qvc_conv_args& a = *srcs[i];
+    QVC_REQUIRE(a.batch == a0.batch && a.out_rows == a0.out_rows && a.x_rows == a0.x_rows && a.cin == a0.cin &&
+                    a.cout == a0.cout && a.opformat == a0.opformat && a.backend == a0.backend && a.bias_bstride == 0 &&
+                    a0.bias_bstride == 0,
+                "conv1d_sum: source %d does not share the geometry of source 0", i);
+    const qvc_epi_segment& g = a.seg[0];
+    QVC_REQUIRE((g.res_op.ptr != nullptr) == from_op && (g.res.ptr != nullptr) == (a0.seg[0].res.ptr != nullptr),
+                "conv1d_sum: every source must give its residual the same way (res, res_op or none)");
+    const qvc_tensor* ts[2] = {&g.res, &g.res_op};
+    for (const qvc_tensor* t : ts)
+      if (t->ptr) QVC_REQUIRE(t->ld % 8 == 0 && t->bstride % 8 == 0 && ((uintptr_t)t->ptr & 15) == 0,
+                              "conv1d_sum: residual of source %d not 8-element / 16-byte aligned", i);
+    ep->xres[i - 1] = make_tref(g.res);
+    ep->xres_op[i - 1] = make_tref(g.res_op);
+    ep->xres_inv_slope[i - 1] = g.res_inv_slope;
+    ep->xbias[i - 1] = a.bias;
+  }
   return QVC_OK;
 }
 

@@ -40,33 +40,44 @@ using namespace tc;
 constexpr int MAXG = 4;                   // output-channel chunks per tile
 constexpr int MAXGROUPS = 10;             // output-channel groups per layer
 
-struct alignas(64) TcParams {
+constexpr int MAXSRC = QVC_MAX_SUM_SOURCES;
+
+// one (input series, filter) pair; an ordinary convolution has one, qvc_conv1d_sum up to MAXSRC
+struct alignas(64) Src1 {
   CUtensorMap mx;                          // x as (channel, frame, utterance)
   CUtensorMap mw;                          // w as (tap*cin + channel, output channel)
   int32_t cin, k, dil, pad_left;
+  int32_t slab_boxes, slab_box_rows;       // slab = slab_boxes TMA boxes of slab_box_rows frames
+  // Structured zeros of the filter (qvc_conv_args.tap_split; only read by the TAPS = true instances): channel chunks
+  // from split_chunk on are input half q = 1; taps[h] packs, for output half h (2 = both), the tap range of input half q
+  // as nibbles: lo at bits 8q, hi at bits 8q + 4.
+  int32_t split_chunk;
+  uint32_t taps[3];
+};
+
+struct alignas(64) TcParams {
+  Src1 src[MAXSRC];
+  int32_t nsrc;
   int32_t ntime;                           // N: frames per tile (multiple of 32, <= 256)
   int32_t ntb;                             // frame blocks per utterance
   int32_t ngroups, ntiles;
   int32_t gsize[MAXGROUPS];                // chunks of each group
   int32_t row0[MAXGROUPS][MAXG];           // filter row (GEMM column n) on lane 0 of each chunk
   int32_t valid[MAXGROUPS][MAXG];          // live lanes of each chunk
-  int32_t slab_boxes, slab_box_rows;       // slab = slab_boxes TMA boxes of slab_box_rows frames
   int32_t slab_stages, w_stages;
   uint32_t slab_stage_bytes, w_stage_bytes;
   int32_t debug;                           // diagnostics only (QVC_TC_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue I/O
+  int32_t cout_half;                       // TAPS: first filter row of output half 1
+  int32_t batch;
   EpiParams ep;
-  // Structured zeros of the filter (qvc_conv_args.tap_split; only read by the TAPS = true instances, at the end of the
-  // struct so that every other launch sees the layout and code it always had): channel chunks from split_chunk on are
-  // input half q = 1; taps[h] packs, for output half h (2 = both), the tap range of input half q as nibbles: lo at
-  // bits 8q, hi at bits 8q + 4.
-  int32_t split_chunk, cout_half;
-  uint32_t taps[3];
 };
 
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
-template <int OPF, int EPI, bool TAPS>
+// SUM (qvc_conv1d_sum): the K loop runs over p.nsrc sources into one accumulator, multi-residual epilogue; every other
+// instance has exactly one source (the loops over sources collapse at compile time).
+template <int OPF, int EPI, bool TAPS, bool SUM>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ESIZE = opf_is16(OPF) ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;            // channels per K block
@@ -83,10 +94,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_full = empty_w + 8 * p.w_stages, tmem_empty = tmem_full + 16;
   const uint32_t tmem_slot = tmem_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  int32_t* live_s = reinterpret_cast<int32_t*>(tmem_slot_ptr + 4);       // ragged batches: copy of ep.live
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_cchunks = p.cin / KC;
   const int N = p.ntime;
+  const int nsrc = SUM ? p.nsrc : 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * p.slab_stages + 2 * p.w_stages + 2; ++i) mbar_init(bar0 + 8 * i, 1);
@@ -108,13 +120,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   // loop's tail); nothing above touched global memory, everything below waits for the previous grid.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.ep.live != nullptr) {
+    load_live_cache(p.ep, p.batch, live_s);
+    __syncthreads();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mx) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
-      const uint32_t slab_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
+      for (int si = 0; si < nsrc; ++si) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.src[si].mx) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.src[si].mw) : "memory");
+      }
       // stage indices / phase parities are carried incrementally: a runtime integer division per K block
       // on this single thread (I2F / MUFU.RCP chains) cost more than the MMAs it feeds
       uint32_t s = 0, ph = 0, ws = 0, wph = 0;
@@ -123,30 +140,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const int rest = tile / p.ngroups;
         const int tb = rest % p.ntb, b = rest / p.ntb;
         const int t0 = tb * N;
+        if (tile_dead(p.ep, live_s, b, t0)) continue;
         const int gs = p.gsize[gi];
-        uint32_t tp = 0;                           // TAPS: tap ranges of this tile's output half (union if it spans both)
-        if constexpr (TAPS) tp = p.taps[gs > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
-        for (int cc = 0; cc < n_cchunks; ++cc) {
-          mbar_wait(empty_slab + 8 * s, ph ^ 1u);
-          if (p.debug & 1) mbar_arrive(full_slab + 8 * s);
-          else             mbar_expect_tx(full_slab + 8 * s, slab_bytes);
-          for (int i = 0; i < p.slab_boxes && !(p.debug & 1); ++i)
-            tma_load_3d(slab0 + s * p.slab_stage_bytes + i * p.slab_box_rows * ROW_BYTES, &p.mx, full_slab + 8 * s,
-                        cc * KC, t0 - p.pad_left + i * p.slab_box_rows, b);
-          if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
-          int jbeg = 0, jend = p.k - 1;
-          if constexpr (TAPS) {
-            const uint32_t r = cc >= p.split_chunk ? tp >> 8 : tp;
-            jbeg = (int)(r & 15u); jend = (int)((r >> 4) & 15u);
-          }
-          for (int j = jbeg; j <= jend; ++j) {
-            mbar_wait(empty_w + 8 * ws, wph ^ 1u);
-            if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
-            else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
-            for (int ci = 0; ci < gs && !(p.debug & 1); ++ci)
-              tma_load_2d(w0 + ws * p.w_stage_bytes + ci * CHUNK_BYTES, &p.mw, full_w + 8 * ws,
-                          j * p.cin + cc * KC, p.row0[gi][ci]);
-            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
+        for (int si = 0; si < nsrc; ++si) {
+          const Src1& S = p.src[si];
+          const int n_cchunks = S.cin / KC;
+          const uint32_t slab_bytes = (uint32_t)S.slab_boxes * S.slab_box_rows * ROW_BYTES;
+          uint32_t tp = 0;                           // TAPS: tap ranges of this tile's output half (union if it spans both)
+          if constexpr (TAPS) tp = S.taps[gs > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
+          for (int cc = 0; cc < n_cchunks; ++cc) {
+            mbar_wait(empty_slab + 8 * s, ph ^ 1u);
+            if (p.debug & 1) mbar_arrive(full_slab + 8 * s);
+            else             mbar_expect_tx(full_slab + 8 * s, slab_bytes);
+            for (int i = 0; i < S.slab_boxes && !(p.debug & 1); ++i)
+              tma_load_3d(slab0 + s * p.slab_stage_bytes + i * S.slab_box_rows * ROW_BYTES, &S.mx, full_slab + 8 * s,
+                          cc * KC, t0 - S.pad_left + i * S.slab_box_rows, b);
+            if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
+            int jbeg = 0, jend = S.k - 1;
+            if constexpr (TAPS) {
+              const uint32_t r = cc >= S.split_chunk ? tp >> 8 : tp;
+              jbeg = (int)(r & 15u); jend = (int)((r >> 4) & 15u);
+            }
+            for (int j = jbeg; j <= jend; ++j) {
+              mbar_wait(empty_w + 8 * ws, wph ^ 1u);
+              if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
+              else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
+              for (int ci = 0; ci < gs && !(p.debug & 1); ++ci)
+                tma_load_2d(w0 + ws * p.w_stage_bytes + ci * CHUNK_BYTES, &S.mw, full_w + 8 * ws,
+                            j * S.cin + cc * KC, p.row0[gi][ci]);
+              if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
+            }
           }
         }
       }
@@ -162,54 +185,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     // M = 128, N = 256 MMA with both operands in shared memory takes ~190 cycles instead of 128, i.e. the
     // 12 KB of operand reads per MMA run at ~64 B/cycle; batching several K blocks per trip changes nothing.
     uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ait) {
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int gi = tile % p.ngroups;
+      {
+        const int rest = tile / p.ngroups;
+        if (tile_dead(p.ep, live_s, rest / p.ntb, (rest % p.ntb) * N)) continue;
+      }
       const int gs = (p.debug & 2) ? 0 : p.gsize[gi];
       const uint32_t buf = ait & 1u;
       mbar_wait(tmem_empty + 8 * buf, ((ait >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator set
       tc_fence_after();
       const uint32_t dbase = tmem_base + buf * ACC_COLS;
-      uint32_t tp = 0;
-      if constexpr (TAPS) tp = p.taps[p.gsize[gi] > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
-      for (int cc = 0; cc < n_cchunks; ++cc) {
-        mbar_wait(full_slab + 8 * s, ph);
-        const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-        int jbeg = 0, jlast = p.k - 1, jfirst = 0;
-        if constexpr (TAPS) {
-          const uint32_t r = cc >= p.split_chunk ? tp >> 8 : tp;
-          jbeg = (int)(r & 15u); jlast = (int)((r >> 4) & 15u); jfirst = (int)(tp & 15u);
-        }
-        for (int j = jbeg; j <= jlast; ++j) {
-          mbar_wait(full_w + 8 * ws, wph);
-          tc_fence_after();
-          const uint32_t wst = w0 + ws * p.w_stage_bytes;
-          const uint32_t first = (cc == 0 && j == jfirst) ? 0u : 1u;
-          const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * p.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
-          if (elect_one()) {
-            for (int ci = 0; ci < gs; ++ci) {
-              const uint64_t adesc = desc_hi | (uint64_t)(((wst + (uint32_t)ci * CHUNK_BYTES) & 0x3FFFFu) >> 4);
-              const uint32_t d = dbase + (uint32_t)(ci * N);
-              if (p.debug & 16) {
-                // timing experiment only (garbage A): A operand from TMEM -- the other accumulator set
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_ts<OPF>(d, tmem_base + (buf ^ 1u) * ACC_COLS + 8 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
-              } else {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)      // +32 bytes per K step = +2 in the (addr >> 4) field
-                  umma<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
-              }
-            }
-            tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
-            if (j == jlast) tc_commit(empty_slab + 8 * s);
+      for (int si = 0; si < nsrc; ++si) {
+        const Src1& S = p.src[si];
+        const int n_cchunks = S.cin / KC;
+        uint32_t tp = 0;
+        if constexpr (TAPS) tp = S.taps[p.gsize[gi] > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
+        for (int cc = 0; cc < n_cchunks; ++cc) {
+          mbar_wait(full_slab + 8 * s, ph);
+          const uint32_t slab = slab0 + s * p.slab_stage_bytes;
+          int jbeg = 0, jlast = S.k - 1, jfirst = 0;
+          if constexpr (TAPS) {
+            const uint32_t r = cc >= S.split_chunk ? tp >> 8 : tp;
+            jbeg = (int)(r & 15u); jlast = (int)((r >> 4) & 15u); jfirst = (int)(tp & 15u);
           }
-          __syncwarp();
-          if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
+          for (int j = jbeg; j <= jlast; ++j) {
+            mbar_wait(full_w + 8 * ws, wph);
+            tc_fence_after();
+            const uint32_t wst = w0 + ws * p.w_stage_bytes;
+            const uint32_t first = (si == 0 && cc == 0 && j == jfirst) ? 0u : 1u;
+            const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * S.dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+              for (int ci = 0; ci < gs; ++ci) {
+                const uint64_t adesc = desc_hi | (uint64_t)(((wst + (uint32_t)ci * CHUNK_BYTES) & 0x3FFFFu) >> 4);
+                const uint32_t d = dbase + (uint32_t)(ci * N);
+                if (p.debug & 16) {
+                  // timing experiment only (garbage A): A operand from TMEM -- the other accumulator set
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_ts<OPF>(d, tmem_base + (buf ^ 1u) * ACC_COLS + 8 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                } else {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)      // +32 bytes per K step = +2 in the (addr >> 4) field
+                    umma<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                }
+              }
+              tc_commit(empty_w + 8 * ws);            // filter stage free once these MMAs retire
+              if (j == jlast) tc_commit(empty_slab + 8 * s);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
+          }
+          if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
         }
-        if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
       }
       if (elect_one()) tc_commit(tmem_full + 8 * buf);
       __syncwarp();
+      ++ait;
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -220,11 +252,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     const int col_end = h == 0 ? ((nblk + 1) >> 1) << 5 : N;
     const int lic = q * 32 + lane;                 // lane within the 128-channel chunk
     uint32_t ait = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ait) {
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int gi = tile % p.ngroups;
       const int rest = tile / p.ngroups;
       const int tb = rest % p.ntb, b = rest / p.ntb;
       const int t0 = tb * N;
+      if (tile_dead(p.ep, live_s, b, t0)) continue;
       const int gs = p.gsize[gi];
       const uint32_t buf = ait & 1u;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
@@ -242,32 +275,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           k.c = k.ok ? c : 0;
           k.b = b;
           k.lim = lim;
-          k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
+          if constexpr (SUM) k.bias = sum_bias(p.ep, b, n, k.ok);
+          else               k.bias = (p.ep.bias && k.ok) ? p.ep.bias[(int64_t)b * p.ep.bias_bs + n] : 0.f;
           return true;
         };
+        constexpr int SB = SUM ? 32 : 64;                          // frames per superblock (SUM: three residual streams)
         auto frames_at = [&](int col) -> int {                     // live frames of the superblock starting at col
           if (p.debug & 4) return 0;
           const int left = min(col_end - col, p.ep.out_rows - (t0 + col));
-          return left < 64 ? left : 64;
+          return left < SB ? left : SB;
         };
-        float r[64];
+        float r[SUM ? 96 : 64];
         LinCtx k;
         // first superblock of the tile: loads in flight before the accumulator is complete
         bool primed = false;
         if (context(0, k)) {
           const int nv = frames_at(col_begin);
-          if (nv > 0) lin_load<OPF>(k, t0 + col_begin, nv, r);
+          if (nv > 0) {
+            if constexpr (SUM) sum_load<OPF>(p.ep, k, t0 + col_begin, nv, r);
+            else               lin_load<OPF>(k, t0 + col_begin, nv, r);
+          }
           primed = true;
         }
         mbar_wait(tmem_full + 8 * buf, (ait >> 1) & 1u);
         tc_fence_after();
         for (int ci = 0; ci < gs; ++ci) {
           if (!context(ci, k)) continue;
-          for (int col = col_begin; col < col_end; col += 64) {
+          for (int col = col_begin; col < col_end; col += SB) {
             const int nv = frames_at(col);
             if (nv <= 0) break;
-            if (!(primed && ci == 0 && col == col_begin)) lin_load<OPF>(k, t0 + col, nv, r);
-            lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)(ci * N + col));
+            if constexpr (SUM) {
+              if (!(primed && ci == 0 && col == col_begin)) sum_load<OPF>(p.ep, k, t0 + col, nv, r);
+              sum_finish<OPF>(p.ep, k, t0 + col, nv, r, tbase + (uint32_t)(ci * N + col));
+            } else {
+              if (!(primed && ci == 0 && col == col_begin)) lin_load<OPF>(k, t0 + col, nv, r);
+              lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)(ci * N + col));
+            }
           }
         }
       } else {
@@ -295,6 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
+      ++ait;
     }
   }
 
@@ -365,11 +409,11 @@ bool prof_next(cudaEvent_t* e0, cudaEvent_t* e1) {
   return true;
 }
 
-template <int OPF, int EPI, bool TAPS>
+template <int OPF, int EPI, bool TAPS, bool SUM = false>
 int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
   static std::atomic<bool> attr_done[MAX_DEVICES];
   if (first_use_on_device(attr_done))
-    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<OPF, EPI, TAPS, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -383,7 +427,7 @@ int launch_variant(const TcParams& p, int grid, size_t smem, cudaStream_t stream
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = prof_next(&e0, &e1);
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e0, stream));
-  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<OPF, EPI, TAPS>, p));
+  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<OPF, EPI, TAPS, SUM>, p));
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e1, stream));
   return post_launch("conv_tc_kernel");
 }
@@ -403,10 +447,12 @@ int tc_sm_count() {
 int tc_env_int(const char* name, int dflt) { return env_int(name, dflt); }
 bool tc_prof_next(cudaEvent_t* e0, cudaEvent_t* e1) { return prof_next(e0, e1); }
 
-int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
-  // layers with an even number of 128-channel chunks and long series go to the CTA-pair kernel
+// Sum of nsrc >= 1 convolutions into one accumulator (nsrc == 1, sum == false: an ordinary convolution; srcs[0]
+// carries the epilogue).  Layers with an even number of 128-channel chunks and long series go to the CTA-pair kernel.
+int launch_conv_tc_any(const qvc_conv_args* const* srcs, int nsrc, bool sum, cudaStream_t stream) {
+  const qvc_conv_args& a = *srcs[0];
   {
-    const int st = launch_conv_tc2(a, stream);
+    const int st = launch_conv_tc2_sum(srcs, nsrc, sum, stream);
     if (st != QVC_ERR_UNSUPPORTED) return st;
   }
   EncodeTiledFn encode = get_encode();
@@ -416,14 +462,19 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   }
   const int esize = (int)opformat_bytes(a.opformat);
   const int kc = ROW_BYTES / esize;
-  QVC_REQUIRE(a.cin % kc == 0, "conv1d(tcgen05): cin %d not a multiple of %d", a.cin, kc);
-  QVC_REQUIRE((a.x.ld * esize) % 16 == 0 && ((uintptr_t)a.x.ptr & 15) == 0 && ((uintptr_t)a.w & 15) == 0,
-              "conv1d(tcgen05): x / w must be 16-byte aligned with 16-byte row pitch");
-  QVC_REQUIRE(a.batch == 1 || (a.x.bstride * esize) % 16 == 0, "conv1d(tcgen05): utterance pitch not 16-byte aligned");
+  for (int si = 0; si < nsrc; ++si) {
+    const qvc_conv_args& x = *srcs[si];
+    QVC_REQUIRE(x.cin % kc == 0, "conv1d(tcgen05): cin %d not a multiple of %d", x.cin, kc);
+    QVC_REQUIRE((x.x.ld * esize) % 16 == 0 && ((uintptr_t)x.x.ptr & 15) == 0 && ((uintptr_t)x.w & 15) == 0,
+                "conv1d(tcgen05): x / w must be 16-byte aligned with 16-byte row pitch");
+    QVC_REQUIRE(x.batch == 1 || (x.x.bstride * esize) % 16 == 0, "conv1d(tcgen05): utterance pitch not 16-byte aligned");
+  }
 
   TcParams p{};
   QVC_PROPAGATE(build_epi_params(a, &p.ep));
-  p.cin = a.cin; p.k = a.k; p.dil = a.dil; p.pad_left = a.pad_left;
+  if (sum) QVC_PROPAGATE(add_sum_sources(srcs, nsrc, &p.ep));
+  p.nsrc = nsrc;
+  p.batch = a.batch;
   p.debug = env_int("QVC_TC_DEBUG", 0);
 
   // ---- output-channel chunks (TMEM lanes) and groups ----
@@ -489,25 +540,31 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   p.ntb = (a.out_rows + ntime - 1) / ntime;
   p.ntiles = a.batch * p.ntb * p.ngroups;
 
-  // ---- shared-memory pipeline ----
-  const int halo = (a.k - 1) * a.dil;
-  const int rows = ntime + halo;
-  p.slab_boxes = (rows + 255) / 256;
-  p.slab_box_rows = (((rows + p.slab_boxes - 1) / p.slab_boxes) + 7) & ~7;
-  QVC_REQUIRE(p.slab_box_rows <= 256, "conv1d(tcgen05): slab box too tall");
-  p.slab_stage_bytes = (uint32_t)p.slab_boxes * p.slab_box_rows * ROW_BYTES;
+  // ---- shared-memory pipeline: one slab ring serves every source, sized for the tallest slab ----
+  p.slab_stage_bytes = 0;
+  for (int si = 0; si < nsrc; ++si) {
+    const qvc_conv_args& x = *srcs[si];
+    Src1& S = p.src[si];
+    S.cin = x.cin; S.k = x.k; S.dil = x.dil; S.pad_left = x.pad_left;
+    const int rows = ntime + (x.k - 1) * x.dil;
+    S.slab_boxes = (rows + 255) / 256;
+    S.slab_box_rows = (((rows + S.slab_boxes - 1) / S.slab_boxes) + 7) & ~7;
+    QVC_REQUIRE(S.slab_box_rows <= 256, "conv1d(tcgen05): slab box too tall");
+    const uint32_t bytes = (uint32_t)S.slab_boxes * S.slab_box_rows * ROW_BYTES;
+    if (bytes > p.slab_stage_bytes) p.slab_stage_bytes = bytes;
+  }
   p.w_stage_bytes = (uint32_t)g * CHUNK_BYTES;
   static const int stage_options[][2] = {{3, 6}, {3, 4}, {2, 4}, {2, 3}, {2, 2}, {1, 2}};
   size_t smem = 0;
   bool fits = false;
   const int ss_env = env_int("QVC_TC_SS", 0), ws_env = env_int("QVC_TC_WS", 0);
   if (ss_env >= 1 && ws_env >= 1 && ss_env <= 8 && ws_env <= 12 && ws_env >= 2) {
-    smem = (size_t)ss_env * p.slab_stage_bytes + (size_t)ws_env * p.w_stage_bytes + 1024 + 256;
+    smem = (size_t)ss_env * p.slab_stage_bytes + (size_t)ws_env * p.w_stage_bytes + 1024 + 256 + live_cache_bytes(a);
     if (smem <= (size_t)MAX_SMEM) { p.slab_stages = ss_env; p.w_stages = ws_env; fits = true; }
   }
   for (const auto& opt : stage_options) {
     if (fits) break;
-    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256;
+    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256 + live_cache_bytes(a);
     if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; }
   }
   if (!fits) {
@@ -518,51 +575,67 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   // ---- tensor maps ----
   const CUtensorMapDataType dt = a.opformat == QVC_OPF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : (a.opformat == QVC_OPF_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.x_rows, (cuuint64_t)a.batch};
-    cuuint64_t strides[2] = {(cuuint64_t)a.x.ld * esize,
-                             (cuuint64_t)(a.batch > 1 ? a.x.bstride : (int64_t)a.x_rows * a.x.ld) * esize};
-    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)p.slab_box_rows, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(&p.mx, dt, 3, a.x.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(x) failed: %d", (int)r); return QVC_ERR_CUDA; }
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)a.k * a.cin, (cuuint64_t)a.cout};
-    cuuint64_t strides[1] = {(cuuint64_t)a.k * a.cin * esize};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)CHUNK_M};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&p.mw, dt, 2, const_cast<void*>(a.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
+  for (int si = 0; si < nsrc; ++si) {
+    const qvc_conv_args& x = *srcs[si];
+    Src1& S = p.src[si];
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)x.cin, (cuuint64_t)x.x_rows, (cuuint64_t)x.batch};
+      cuuint64_t strides[2] = {(cuuint64_t)x.x.ld * esize,
+                               (cuuint64_t)(x.batch > 1 ? x.x.bstride : (int64_t)x.x_rows * x.x.ld) * esize};
+      cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)S.slab_box_rows, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = encode(&S.mx, dt, 3, x.x.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(x) failed: %d", (int)r); return QVC_ERR_CUDA; }
+    }
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)x.k * x.cin, (cuuint64_t)x.cout};
+      cuuint64_t strides[1] = {(cuuint64_t)x.k * x.cin * esize};
+      cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)CHUNK_M};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = encode(&S.mw, dt, 2, const_cast<void*>(x.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
+    }
   }
 
-  // structured-zero hint (LINEAR layers whose two output halves are whole chunks): packed tap ranges, TAPS instance
+  // structured-zero hint (LINEAR layers whose two output halves are whole chunks): packed tap ranges, TAPS instance.
+  // A sum uses the TAPS instance whenever ANY source has a hint; sources without one get the full tap range.
   bool taps = false;
-  if (a.tap_split > 0 && a.tap_split % kc == 0 && a.tap_split < a.cin && !paired && (a.cout / 2) % CHUNK_M == 0 && a.k <= 16) {
-    taps = true;
-    p.split_chunk = a.tap_split / kc;
-    p.cout_half = a.cout / 2;
+  p.cout_half = a.cout / 2;
+  for (int si = 0; si < nsrc; ++si) {
+    const qvc_conv_args& x = *srcs[si];
+    if (x.tap_split > 0 && x.tap_split % kc == 0 && x.tap_split < x.cin && !paired && (x.cout / 2) % CHUNK_M == 0 && x.k <= 16) taps = true;
+  }
+  for (int si = 0; si < nsrc && taps; ++si) {
+    const qvc_conv_args& x = *srcs[si];
+    Src1& S = p.src[si];
+    QVC_REQUIRE(x.k <= 16, "conv1d(tcgen05): tap hints need k <= 16 in every source");
+    const bool has = x.tap_split > 0 && x.tap_split % kc == 0 && x.tap_split < x.cin;
+    S.split_chunk = has ? x.tap_split / kc : (1 << 30);
     for (int h = 0; h < 3; ++h) {
       uint32_t w = 0;
       for (int q = 0; q < 2; ++q) {
-        int lo, hi;
-        if (h < 2) { lo = a.tap_lo[h][q]; hi = a.tap_hi[h][q]; }
-        else {
-          lo = a.tap_lo[0][q] < a.tap_lo[1][q] ? a.tap_lo[0][q] : a.tap_lo[1][q];
-          hi = a.tap_hi[0][q] > a.tap_hi[1][q] ? a.tap_hi[0][q] : a.tap_hi[1][q];
+        int lo = 0, hi = x.k - 1;
+        if (has) {
+          if (h < 2) { lo = x.tap_lo[h][q]; hi = x.tap_hi[h][q]; }
+          else {
+            lo = x.tap_lo[0][q] < x.tap_lo[1][q] ? x.tap_lo[0][q] : x.tap_lo[1][q];
+            hi = x.tap_hi[0][q] > x.tap_hi[1][q] ? x.tap_hi[0][q] : x.tap_hi[1][q];
+          }
         }
-        QVC_REQUIRE(lo >= 0 && hi < a.k && lo <= hi, "conv1d: bad tap range [%d, %d] for k = %d", lo, hi, a.k);
+        QVC_REQUIRE(lo >= 0 && hi < x.k && lo <= hi, "conv1d: bad tap range [%d, %d] for k = %d", lo, hi, x.k);
         w |= ((uint32_t)lo | (uint32_t)hi << 4) << (8 * q);
       }
-      p.taps[h] = w;
+      S.taps[h] = w;
     }
   }
   int grid = p.ntiles < tc_sm_count() ? p.ntiles : tc_sm_count();
   const int grid_env = env_int("QVC_TC_GRID", 0);
   if (grid_env >= 1 && grid_env < grid) grid = grid_env;
 #define QVC_TC_DISPATCH(OPF)                                                                         \
+  if (sum) return taps ? launch_variant<OPF, QVC_EPI_LINEAR, true, true>(p, grid, smem, stream)       \
+                       : launch_variant<OPF, QVC_EPI_LINEAR, false, true>(p, grid, smem, stream);     \
   switch (a.epilogue) {                                                                              \
     case QVC_EPI_LINEAR: return taps ? launch_variant<OPF, QVC_EPI_LINEAR, true>(p, grid, smem, stream)    \
                                      : launch_variant<OPF, QVC_EPI_LINEAR, false>(p, grid, smem, stream);  \
@@ -573,6 +646,15 @@ int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
   if (a.opformat == QVC_OPF_F16) { QVC_TC_DISPATCH(QVC_OPF_F16) }
   QVC_TC_DISPATCH(QVC_OPF_TF32)
 #undef QVC_TC_DISPATCH
+}
+
+int launch_conv_tc(const qvc_conv_args& a, cudaStream_t stream) {
+  const qvc_conv_args* one[1] = {&a};
+  return launch_conv_tc_any(one, 1, false, stream);
+}
+
+int launch_conv_tc_sum(const qvc_conv_args* const* srcs, int nsrc, cudaStream_t stream) {
+  return launch_conv_tc_any(srcs, nsrc, true, stream);
 }
 
 }  // namespace qvc

@@ -128,6 +128,62 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return d;
 }
 
+// ---- thread-block clusters / CTA pairs (cta_group::2): shared by conv_tc2.cu and conv_wn.cu ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA, the bytes are counted on the barrier at `bar`
+// (a shared::cluster address -- the leader's)
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at the same offset in both CTAs once all prior MMAs of this thread have retired
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+template <int OPF>
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (opf_is16(OPF)) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 // 32 consecutive TMEM columns of this thread's lane; completion via tmem_wait().
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -220,13 +276,34 @@ __device__ __forceinline__ void lin_load(const LinCtx& k, int t, int nv, float* 
   }
 }
 
+// 16-bit operand-copy residuals only: BOTH 64-frame superblocks of a warp's 128 frames in one burst, two values per
+// register (low half = frame i, high half = frame 64 + i).  The second superblock's loads are then in flight before the
+// accumulator is complete as well -- measured (profiles/r02_summary.md): its exposed latency was what made the c2 layers
+// of the 16-bit modes ~45 us slower than their c1 twins.  Requires 128 live frames and a live channel in every lane.
 template <int OPF>
-__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float* r, uint32_t taddr) {
+__device__ __forceinline__ void lin_load_packed(const LinCtx& k, int t, float* r) {
+  static_assert(opf_is16(OPF), "packed residual loads are for the 2-byte operand formats");
+  using OT = typename OpType<OPF>::type;
+  const EpiSeg& sg = *k.sg;
+  const uint16_t* rp16 = reinterpret_cast<const uint16_t*>(sg.res_op.at<OT>(k.b, t, k.c));
+  const int ld = sg.res_op.ld;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const uint32_t lo = rp16[i * ld], hi = rp16[(64 + i) * ld];
+    r[i] = __uint_as_float(lo | (hi << 16));
+  }
+}
+
+// packed_half: 0 = r holds one value per register (lin_load); 1 / 2 = r was filled by lin_load_packed and this call
+// finishes the first / second superblock (low / high halves)
+template <int OPF>
+__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float* r, uint32_t taddr, int packed_half = 0) {
   using OT = typename OpType<OPF>::type;
   const EpiSeg& sg = *k.sg;
   const bool res_from_op = sg.res_op.present();
   const bool has_res = sg.res.present() || res_from_op, has_acc = sg.accin.present();
   const float alpha = sg.alpha, beta = sg.beta, slope = sg.slope;
+  const float inv = sg.res_inv_slope;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int th = t + 32 * h, nvh = nv - 32 * h;
@@ -234,16 +311,21 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
     float v[32];
     tmem_ld32(taddr + 32 * h, v);
     tmem_wait();
-    float* rr = r + 32 * h;
-    if (res_from_op) {                               // decode the operand copy in place: undo the leaky-relu
-      const float inv = sg.res_inv_slope;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = rr[i];
-        if constexpr (opf_is16(OPF)) x = op16_to_float<OPF>(__float_as_uint(x));
-        rr[i] = x > 0.f ? x : x * inv;
+    const float* rr = r + 32 * h;
+    // residual of element i: fp32 as loaded, or the operand copy decoded (leaky-relu undone) on the fly
+    auto resv = [&](int i) -> float {
+      float x = rr[i];
+      if (res_from_op) {
+        if constexpr (opf_is16(OPF)) {
+          uint32_t bits = __float_as_uint(x);
+          if (packed_half == 2) bits >>= 16;
+          else if (packed_half == 1) bits &= 0xffffu;
+          x = op16_to_float<OPF>(bits);
+        }
+        x = x > 0.f ? x : x * inv;
       }
-    }
+      return x;
+    };
     if (has_res && has_acc) {
       // both streams (last convolution of MRF blocks 2 and 3): the accumulate-into tensor is loaded late, 8 at a time
       const float* ap = sg.accin.at<float>(k.b, th, k.c);
@@ -254,11 +336,11 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = (k.ok && g + i < nvh) ? ap[(g + i) * ld] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, rr[g + i]), a[i]);
+        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, resv(g + i)), a[i]);
       }
     } else if (has_res) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, rr[i]);
+      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, resv(i));
     } else if (has_acc) {
       const float ab = alpha * beta;
 #pragma unroll
@@ -295,6 +377,125 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
       }
     }
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Sum of convolutions (qvc_conv1d_sum): one segment, up to three residual sources, blocks of 32 frames.
+//   v = beta * (alpha * (acc + bias) + res_0 + res_1 + res_2)        (bias = sum of the sources' biases, in LinCtx)
+// sum_load only issues the loads of a block (raw bits, decoded in sum_finish), so the first block of a tile is in
+// flight before the accumulator is complete.
+// ----------------------------------------------------------------------------------------------
+template <int OPF>
+__device__ __forceinline__ void sum_load(const EpiParams& ep, const LinCtx& k, int t, int nv, float* r) {
+  using OT = typename OpType<OPF>::type;
+  const EpiSeg& sg = *k.sg;
+  const bool full = k.all_ok && nv >= 32;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s >= ep.nsum) break;
+    const TRef& ro = s == 0 ? sg.res_op : ep.xres_op[s - 1];
+    const TRef& rf = s == 0 ? sg.res : ep.xres[s - 1];
+    float* rr = r + 32 * s;
+    if (ro.present()) {
+      const OT* rp = ro.at<OT>(k.b, t, k.c);
+      const int ld = ro.ld;
+      if constexpr (opf_is16(OPF)) {
+        const uint16_t* rp16 = reinterpret_cast<const uint16_t*>(rp);
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = __uint_as_float((uint32_t)rp16[i * ld]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = (k.ok && i < nv) ? __uint_as_float((uint32_t)rp16[i * ld]) : 0.f;
+        }
+      } else {
+        const float* rpf = reinterpret_cast<const float*>(rp);
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = rpf[i * ld];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = (k.ok && i < nv) ? rpf[i * ld] : 0.f;
+        }
+      }
+    } else if (rf.present()) {
+      const float* rp = rf.at<float>(k.b, t, k.c);
+      const int ld = rf.ld;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = rp[i * ld];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = (k.ok && i < nv) ? rp[i * ld] : 0.f;
+      }
+    }
+  }
+}
+
+template <int OPF>
+__device__ __forceinline__ void sum_finish(const EpiParams& ep, const LinCtx& k, int t, int nv, float* r, uint32_t taddr) {
+  using OT = typename OpType<OPF>::type;
+  const EpiSeg& sg = *k.sg;
+  const bool from_op = sg.res_op.present();
+  const bool has_res = from_op || sg.res.present();
+  float v[32];
+  tmem_ld32(taddr, v);
+  tmem_wait();
+  if (from_op) {                                   // operand copies hold leaky_relu(x): undo it
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      if (s >= ep.nsum) break;
+      const float inv = s == 0 ? sg.res_inv_slope : ep.xres_inv_slope[s - 1];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = r[32 * s + i];
+        if constexpr (opf_is16(OPF)) x = op16_to_float<OPF>(__float_as_uint(x));
+        r[32 * s + i] = x > 0.f ? x : x * inv;
+      }
+    }
+  }
+  const float alpha = sg.alpha, beta = sg.beta, slope = sg.slope;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float a = has_res ? fmaf(alpha, v[i] + k.bias, r[i]) : alpha * (v[i] + k.bias);
+    if (has_res && ep.nsum > 1) a += r[32 + i];
+    if (has_res && ep.nsum > 2) a += r[64 + i];
+    v[i] = beta * a;
+  }
+  const int nlive = k.lim - t;
+  const bool full = k.all_ok && nv >= 32;
+  if (sg.raw.present()) {
+    float* wp = sg.raw.at<float>(k.b, t, k.c);
+    const int ld = sg.raw.ld;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) wp[i * ld] = v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (k.ok && i < nv) wp[i * ld] = v[i];
+    }
+  }
+  if (sg.op.present()) {
+    OT* op = sg.op.at<OT>(k.b, t, k.c);
+    const int ld = sg.op.ld;
+    if (full && nlive >= 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) op[i * ld] = to_operand<OPF>(fmaxf(v[i], v[i] * slope));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (k.ok && i < nv) op[i * ld] = to_operand<OPF>(i < nlive ? leaky(v[i], slope) : 0.f);
+    }
+  }
+}
+
+// bias of a sum of convolutions: the sources' bias vectors added in source order
+__device__ __forceinline__ float sum_bias(const EpiParams& ep, int b, int n, bool ok) {
+  float bias = (ep.bias && ok) ? ep.bias[(int64_t)b * ep.bias_bs + n] : 0.f;
+  if (ep.nsum > 1 && ep.xbias[0] && ok) bias += ep.xbias[0][n];
+  if (ep.nsum > 2 && ep.xbias[1] && ok) bias += ep.xbias[1][n];
+  return bias;
 }
 
 // tanh(x) * sigmoid(y) with two ex2 and ONE rcp:  (e^{2x} - 1) / ((e^{2x} + 1) (1 + e^{-y})).
@@ -404,5 +605,6 @@ void tc_reserve_sms(int n);         // per host thread; see conv_tc.cu
 int tc_env_int(const char* name, int dflt);
 bool tc_prof_next(cudaEvent_t* e0, cudaEvent_t* e1);
 int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream);     // conv_tc2.cu; QVC_ERR_UNSUPPORTED = not applicable
+int launch_conv_tc2_sum(const qvc_conv_args* const* srcs, int nsrc, bool sum, cudaStream_t stream);
 
 }  // namespace qvc

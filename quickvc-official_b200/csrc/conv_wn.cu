@@ -45,29 +45,14 @@ struct alignas(64) WnParams {
   int32_t ntb, ntiles;
   int32_t slab_box_rows, slab_stages, w_stages;
   uint32_t slab_stage_bytes;
-  int32_t out_rows;
+  int32_t out_rows, batch;
+  int32_t debug;                           // timing experiments only (QVC_WN_DEBUG, results are garbage): 1 no gate epilogue body,
+                                           // 2 no res_skip epilogue loads, 4 no res_skip epilogue body, 8 no GEMM 1, 16 no GEMM 2
   const float* gate_bias;                  // [2H] (+ per-utterance stride)
   int64_t gate_bias_bs;
   EpiParams ep;                            // res_skip epilogue (LINEAR, 1 or 2 segments)
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // wait that also acquires at cluster scope: the data guarded by the barrier was written by the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -80,39 +65,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (spins > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc2_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-template <int OPF>
-__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (opf_is16(OPF)) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
   }
 }
 __device__ __forceinline__ void st_cluster_b32(uint32_t cluster_addr, uint32_t v) {
@@ -143,6 +95,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
   const uint32_t acts_ready = acc2_full + 8, acc2_empty = acts_ready + 8;
   const uint32_t tmem_slot = acc2_empty + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  int32_t* live_s = reinterpret_cast<int32_t*>(tmem_slot_ptr + 4);       // ragged batches: copy of ep.live
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -167,6 +120,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ragged batches: every warp role walks the same list of live tiles (tiles wholly past their utterance's end are skipped)
+  if (p.ep.live != nullptr) {
+    load_live_cache(p.ep, p.batch, live_s);
+    __syncthreads();
+  }
+  auto next_live = [&](int tile) -> int {
+    while (tile < p.ntiles && tile_dead(p.ep, live_s, tile / p.ntb, (tile % p.ntb) * PN)) tile += npairs;
+    return tile;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -205,11 +168,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
           if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
         }
       };
-      int tile = pair;
+      int tile = next_live(pair);
       if (tile < p.ntiles) load_g1(tile);
-      for (; tile < p.ntiles; tile += npairs) {
+      while (tile < p.ntiles) {
         load_g2();
-        if (tile + npairs < p.ntiles) load_g1(tile + npairs);
+        tile = next_live(tile + npairs);
+        if (tile < p.ntiles) load_g1(tile);
       }
     }
   } else if (warp == 1) {
@@ -230,11 +194,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
             const uint64_t bdesc = desc_hi | (uint64_t)(((slab + (uint32_t)j * ROW_BYTES) & 0x3FFFFu) >> 4);
             const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * W_STAGE) & 0x3FFFFu) >> 4);
             if (elect_one()) {
+              if (!(p.debug & 8)) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma2<OPF>(tmem_base, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                for (int ks = 0; ks < 4; ++ks) umma2<OPF>(tmem_base, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma2<OPF>(tmem_base + PN, adesc + (CHUNK_BYTES >> 4) + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma2<OPF>(tmem_base + PN, adesc + (CHUNK_BYTES >> 4) + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              }
               tc2_commit(empty_w + 8 * ws);
               if (j == p.k - 1) tc2_commit(empty_slab + 8 * s);
             }
@@ -254,11 +220,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
           const uint64_t bdesc = desc_hi | (uint64_t)(((acts0 + (uint32_t)cc * ACTS_CHUNK) & 0x3FFFFu) >> 4);
           const uint64_t adesc = desc_hi | (uint64_t)(((w0 + ws * W_STAGE) & 0x3FFFFu) >> 4);
           if (elect_one()) {
+            if (!(p.debug & 16)) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma2<OPF>(tmem_base + 2 * PN, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              for (int ks = 0; ks < 4; ++ks) umma2<OPF>(tmem_base + 2 * PN, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma2<OPF>(tmem_base + 3 * PN, adesc + (CHUNK_BYTES >> 4) + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma2<OPF>(tmem_base + 3 * PN, adesc + (CHUNK_BYTES >> 4) + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+            }
             tc2_commit(empty_w + 8 * ws);
           }
           __syncwarp();
@@ -268,16 +236,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
         __syncwarp();
       };
       uint32_t it = 0;
-      int tile = pair;
+      int tile = next_live(pair);
       if (tile < p.ntiles) gemm1();
-      for (; tile < p.ntiles; tile += npairs, ++it) {
+      for (; tile < p.ntiles; ++it) {
         // activations of this tile written by all 16 epilogue warps (=> acc1 drained too), acc2 drained by the
         // previous tile's res_skip epilogue
         mbar_wait_cluster(acts_ready, it & 1u);
         mbar_wait(acc2_empty, (it & 1u) ^ 1u);
         tc_fence_after();
         gemm2();
-        if (tile + npairs < p.ntiles) gemm1();
+        tile = next_live(tile + npairs);
+        if (tile < p.ntiles) gemm1();
       }
     }
   } else {
@@ -295,14 +264,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
     const uint32_t acts_dst = map_to_cta(acts0, (uint32_t)h) + (uint32_t)(gch / KC) * ACTS_CHUNK;
     const uint32_t col_byte = (uint32_t)(gch % KC) * ESIZE;           // byte offset within the 128-byte row
     uint32_t it = 0;
-    for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+    for (int tile = next_live(pair); tile < p.ntiles; tile = next_live(tile + npairs), ++it) {
       const int tb = tile % p.ntb, b = tile / p.ntb;
       const int t0 = tb * PN;
       const uint32_t par = it & 1u;
       // ---- gate epilogue: acc1 -> activations in shared memory (own or peer CTA) ----
       mbar_wait(acc1_full, par);
       tc_fence_after();
-      if (gate_warp_live) {
+      if (gate_warp_live && !(p.debug & 1)) {
         const float* gb = p.gate_bias + (int64_t)b * p.gate_bias_bs;
         const float b_lo = gate_ok ? gb[gch] : 0.f, b_hi = gate_ok ? gb[p.hid + gch] : 0.f;
 #pragma unroll
@@ -355,13 +324,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
       int nv = p.out_rows - (t0 + col);
       nv = nv < 0 ? 0 : (nv > HN ? HN : nv);
       float r[64];
-      if (live[0] && nv > 0) lin_load<OPF>(kx[0], t0 + col, nv, r);           // in flight before the accumulator is complete
+      if (p.debug & 4) nv = 0;
+      if (live[0] && nv > 0 && !(p.debug & 2)) lin_load<OPF>(kx[0], t0 + col, nv, r);           // in flight before the accumulator is complete
       mbar_wait(acc2_full, par);
       tc_fence_after();
       if (nv > 0) {
         if (live[0]) lin_finish<OPF>(kx[0], t0 + col, nv, r, tlane + (uint32_t)(2 * PN + col));
         if (live[1]) {
-          lin_load<OPF>(kx[1], t0 + col, nv, r);
+          if (!(p.debug & 2)) lin_load<OPF>(kx[1], t0 + col, nv, r);
           lin_finish<OPF>(kx[1], t0 + col, nv, r, tlane + (uint32_t)(3 * PN + col));
         }
       }
@@ -445,8 +415,9 @@ extern "C" int qvc_wn_layer(const qvc_conv_args* gi, const qvc_conv_args* rs, qv
   WnParams p{};
   QVC_PROPAGATE(build_epi_params(*rs, &p.ep));
   p.hid = H; p.k = gi->k; p.pad_left = gi->pad_left; p.rs_cout = rs->cout;
-  p.ntb = ntb; p.ntiles = ntiles; p.out_rows = gi->out_rows;
+  p.ntb = ntb; p.ntiles = ntiles; p.out_rows = gi->out_rows; p.batch = gi->batch;
   p.gate_bias = gi->bias; p.gate_bias_bs = gi->bias_bstride;
+  p.debug = tc_env_int("QVC_WN_DEBUG", 0);
   const int halo = gi->k - 1;
   p.slab_box_rows = (HN + halo + 7) & ~7;
   p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
@@ -455,7 +426,7 @@ extern "C" int qvc_wn_layer(const qvc_conv_args* gi, const qvc_conv_args* rs, qv
   size_t smem = 0;
   bool fits = false;
   for (const auto& opt : stage_options) {
-    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * W_STAGE + (size_t)n_cchunks * ACTS_CHUNK + 1024 + 256;
+    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * W_STAGE + (size_t)n_cchunks * ACTS_CHUNK + 1024 + 256 + live_cache_bytes(*rs);
     if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
   }
   if (!fits) return QVC_ERR_UNSUPPORTED;

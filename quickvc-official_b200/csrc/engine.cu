@@ -44,22 +44,53 @@ struct Buffers {
   void *unitO, *xO, *xO2, *actsO, *skipO, *zO;
   float *noiseT, *xR, *skipR, *zR, *tapA, *tapB, *condvec, *g;
   void* spk_ws; size_t spk_ws_bytes;
-  // per decoder sub-batch
-  void *aO, *x1O, *t1O, *xaO, *uO, *y1O, *t2O, *yaO, *pO;
-  float *x1R, *xaR, *sum1R, *y1R, *yaR, *sum2R, *cpR;
+  // per decoder sub-batch; [3]: one per ResBlock of an MRF stage (the three blocks' last convolutions run as ONE sum
+  // of convolutions, so their inputs and residual streams are alive together)
+  void *aO, *x1O, *t1O[3], *xaO[3], *uO, *y1O, *t2O[3], *yaO[3], *pO;
+  float *x1R, *xaR[3], *sum1R, *y1R, *yaR[3], *sum2R, *cpR;
 };
+
+// Utterances per chunk of the WN stacks (prior encoder, flow).  Default: the whole batch.  QVC_WN_CHUNK=n runs them n
+// utterances at a time so that the fp32 residual / skip streams of a chunk stay L2-resident between layers -- measured
+// on B200 (profiles/r02_summary.md): at B = 64 x 10 s chunks of 32 / 16 / 8 utterances cost +3 % / +9 % / +45 % of the
+// step in tf32 (+2.5 / +12 / +54 % in fp16): a fused WN layer is bound by its serial per-tile chain and by streaming its
+// filters from L2, not by HBM, and short launches lose the overlap between consecutive tiles.
+int wn_chunk_utts(int B, int T) {
+  static const int env = [] {
+    const char* e = getenv("QVC_WN_CHUNK");
+    return e ? atoi(e) : 0;
+  }();
+  (void)T;
+  return (env <= 0 || env > B) ? B : env;
+}
 
 int pick_chunk(const qvc_model* m, int B, int T) {
   int cb = m->chunk_utts;
   if (cb <= 0) {
     // Whole batch per launch unless the decoder working set would pass ~24 GB (measured on B200,
     // profiles/r01_v1_summary.md: sub-batching for L2 residency starves the grid and is 2.2x slower).
-    // Per utterance: ~14 live series of 20 T rows x 128 channels (or 5 T x 256), 4 bytes each.
-    const double per_utt = 14.0 * 20.0 * T * C_UP1 * 4.0;
+    // Per utterance: ~24 live series of 20 T rows x 128 channels (or 5 T x 256), 4 bytes each.
+    const double per_utt = 24.0 * 20.0 * T * C_UP1 * 4.0;
     cb = (int)(24.0 * 1024 * 1024 * 1024 / (per_utt > 1 ? per_utt : 1));
     if (cb < 1) cb = 1;
   }
   return cb > B ? B : cb;
+}
+
+// The 16-bit modes of the tensor-core back end keep the residual streams of the MRF only as the operand copy the next
+// convolution reads anyway (qvc_epi_segment.res_op): the c2 layers are memory-bound there and this halves their
+// traffic.  In the fp32 (TF32) mode the residual streams stay unrounded fp32.
+int residual_from_operand_mode() {                // 0: never, 1 (default): 16-bit modes, 2: experiment -- TF32 mode too
+  static const int mode = [] {
+    const char* e = getenv("QVC_RES_FROM_OP");
+    return e ? atoi(e) : 1;
+  }();
+  return mode;
+}
+bool residual_from_operand(const qvc_model* m) {
+  const int mode = residual_from_operand_mode();
+  if (m->backend != QVC_BACKEND_TCGEN05) return false;
+  return (mode >= 1 && opf_is16(m->opformat)) || (mode >= 2 && m->opformat == QVC_OPF_TF32);
 }
 
 size_t carve(const qvc_model* m, const Shapes& s, int mel_batch, int mel_frames, bool with_spk,
@@ -82,14 +113,24 @@ size_t carve(const qvc_model* m, const Shapes& s, int mel_batch, int mel_frames,
   const size_t c = (size_t)s.cb, T = (size_t)s.T;
   const size_t r0 = c * UP0 * T, r1 = c * UP0 * UP1 * T, rp = c * (UP0 * UP1 * T + 1);
   b->aO = a.take(c * T * C_PRE * E);
+  // the fp32 residual streams exist only where the mode keeps them (the 16-bit tensor-core modes read the residual back
+  // from the operand copy, residual_from_operand); the fp32 running sum only on the FMA back end
+  const bool tc = m->backend == QVC_BACKEND_TCGEN05;
+  const bool need_r = !residual_from_operand(m);
   b->x1R = (float*)a.take(r0 * C_UP0 * 4);   b->x1O = a.take(r0 * C_UP0 * E);
-  b->t1O = a.take(r0 * C_UP0 * E);
-  b->xaR = (float*)a.take(r0 * C_UP0 * 4);   b->xaO = a.take(r0 * C_UP0 * E);
-  b->sum1R = (float*)a.take(r0 * C_UP0 * 4); b->uO = a.take(r0 * C_UP0 * E);
+  for (int r = 0; r < 3; ++r) {
+    b->t1O[r] = a.take(r0 * C_UP0 * E);
+    b->xaR[r] = (float*)a.take(need_r || r == 0 ? r0 * C_UP0 * 4 : 0);
+    b->xaO[r] = a.take(r0 * C_UP0 * E);
+  }
+  b->sum1R = (float*)a.take(tc ? 0 : r0 * C_UP0 * 4); b->uO = a.take(r0 * C_UP0 * E);
   b->y1R = (float*)a.take(r1 * C_UP1 * 4);   b->y1O = a.take(r1 * C_UP1 * E);
-  b->t2O = a.take(r1 * C_UP1 * E);
-  b->yaR = (float*)a.take(r1 * C_UP1 * 4);   b->yaO = a.take(r1 * C_UP1 * E);
-  b->sum2R = (float*)a.take(r1 * C_UP1 * 4);
+  for (int r = 0; r < 3; ++r) {
+    b->t2O[r] = a.take(r1 * C_UP1 * E);
+    b->yaR[r] = (float*)a.take(need_r || r == 0 ? r1 * C_UP1 * 4 : 0);
+    b->yaO[r] = a.take(r1 * C_UP1 * E);
+  }
+  b->sum2R = (float*)a.take(tc ? 0 : r1 * C_UP1 * 4);
   b->pO = a.take(rp * C_UP1 * E);
   b->cpR = (float*)a.take(rp * C_POST * 4);
   return a.off;
@@ -162,18 +203,6 @@ qvc_conv_args paired_args(const Ctx& c, int li, const void* x, int64_t bs, int b
   return a;
 }
 
-// bf16 mode on the tensor-core back end keeps the residual streams of the MRF only as the operand copy the next
-// convolution reads anyway (qvc_epi_segment.res_op): the c2 layers are memory-bound there and this halves their
-// traffic.  In the fp32 (TF32) mode the residual streams stay unrounded fp32.
-bool residual_from_operand(const Ctx& c) {
-  static const int mode = [] {                    // 0: never, 1 (default): bf16 mode, 2: experiment -- TF32 mode too
-    const char* e = getenv("QVC_RES_FROM_OP");
-    return e ? atoi(e) : 1;
-  }();
-  if (c.m->backend != QVC_BACKEND_TCGEN05) return false;
-  return (mode >= 1 && opf_is16(c.m->opformat)) || (mode >= 2 && c.m->opformat == QVC_OPF_TF32);
-}
-
 // One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack
 // input; on return skipO holds the operand copy of the summed skip output.
 int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, int n_layers,
@@ -225,10 +254,15 @@ int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, in
 }
 
 // MRF = mean of three ResBlock1 (models.py:378-384, modules.py:147-154) on a sub-batch.
-int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void* x1O, void* tO,
-            float* xaR, void* xaO, float* sumR, qvc_tensor final_op, float final_slope, float* final_raw) {
+// tcgen05 back end: the last convolution of the three blocks (convs2[2], modules.py:153-154) runs as ONE sum of
+// convolutions (qvc_conv1d_sum) -- xs / 3 = (1/3) sum_r (x_r + c2_r(t_r)) accumulates in tensor memory, the fp32 running
+// sum of the reference (models.py:380-383) never exists in HBM.  FMA back end: the blocks chain through `accin`.
+int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void* x1O, void* const* tO,
+            float* const* xaR, void* const* xaO, float* sumR, qvc_tensor final_op, float final_slope, float* final_raw) {
   const int64_t bs = (int64_t)rows * ch;
-  const bool rfo = residual_from_operand(c);
+  const bool rfo = residual_from_operand(c.m);
+  const bool fused_sum = c.m->backend == QVC_BACKEND_TCGEN05;
+  qvc_conv_args last[3];
   for (int r = 0; r < 3; ++r) {
     const int lb = l_res0 + 6 * r;
     const float* srcR = x1R;
@@ -241,11 +275,11 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
                            : layer_args(c, lb + j, tens(srcO, bs, ch), cb, rows, rows);
       a.seg[0] = seg(0, w1);
       a.seg[0].slope = 0.1f;
-      a.seg[0].op = tens(tO, bs, w1);
+      a.seg[0].op = tens(tO[r], bs, w1);
       QVC_PROPAGATE(run(c, a));
 
-      qvc_conv_args d = p2 ? paired_args(c, lb + 3 + j, tO, bs, cb, rows, ch)
-                           : layer_args(c, lb + 3 + j, tens(tO, bs, ch), cb, rows, rows);
+      qvc_conv_args d = p2 ? paired_args(c, lb + 3 + j, tO[r], bs, cb, rows, ch)
+                           : layer_args(c, lb + 3 + j, tens(tO[r], bs, ch), cb, rows, rows);
       d.seg[0] = seg(0, w2);
       if (rfo) {
         d.seg[0].res_op = tens(srcO, bs, w2);       // leaky_relu(x, 0.1) in operand format
@@ -254,10 +288,13 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
         d.seg[0].res = tens(srcR, bs, w2);
       }
       if (j < 2) {
-        if (!rfo) d.seg[0].raw = tens(xaR, bs, w2);
-        d.seg[0].op = tens(xaO, bs, w2);
+        if (!rfo) d.seg[0].raw = tens(xaR[r], bs, w2);
+        d.seg[0].op = tens(xaO[r], bs, w2);
         d.seg[0].slope = 0.1f;
-        srcR = xaR; srcO = xaO;
+        srcR = xaR[r]; srcO = xaO[r];
+        QVC_PROPAGATE(run(c, d));
+      } else if (fused_sum) {
+        last[r] = d;                                // issued below, all three blocks at once
       } else {
         d.seg[0].beta = 1.f / 3.f;
         if (r > 0) d.seg[0].accin = tens(sumR, bs, w2);
@@ -269,9 +306,21 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
           d.seg[0].slope = final_slope;
           if (final_raw) d.seg[0].raw = tens(final_raw, bs, w2);
         }
+        QVC_PROPAGATE(run(c, d));
       }
-      QVC_PROPAGATE(run(c, d));
     }
+  }
+  if (fused_sum) {
+    // the three sources share one form (plain or frame-paired: cout decides the view of the output tensors)
+    const int w2 = last[0].cout;
+    QVC_REQUIRE(last[1].cout == w2 && last[2].cout == w2, "MRF: the ResBlocks' last convolutions differ in form");
+    last[0].seg[0].beta = 1.f / 3.f;
+    last[0].seg[0].op = final_op;
+    last[0].seg[0].op.ld = final_op.ld * (w2 / ch);
+    last[0].seg[0].slope = final_slope;
+    if (final_raw) last[0].seg[0].raw = tens(final_raw, bs, w2);
+    const qvc_conv_args* srcs[3] = {&last[0], &last[1], &last[2]};
+    QVC_PROPAGATE(qvc_conv1d_sum(srcs, 3, (qvc_stream_t)c.st));
   }
   return QVC_OK;
 }
@@ -305,7 +354,7 @@ int run_decoder(const Ctx& whole, const Buffers& bf, const Shapes& s, const void
       qvc_conv_args a = layer_args(c, L_UPS + 0, tens(bf.aO, (int64_t)T * C_PRE, C_PRE), cb, T, T);
       a.seg[0] = seg(0, UP0 * C_UP0);
       a.seg[0].slope = 0.1f;
-      if (!residual_from_operand(c) || (taps && taps->ups0)) a.seg[0].raw = tens(bf.x1R, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
+      if (!residual_from_operand(c.m) || (taps && taps->ups0)) a.seg[0].raw = tens(bf.x1R, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
       a.seg[0].op = tens(bf.x1O, (int64_t)T * UP0 * C_UP0, UP0 * C_UP0);
       QVC_PROPAGATE(run(c, a));
       if (taps && taps->ups0)
@@ -315,9 +364,9 @@ int run_decoder(const Ctx& whole, const Buffers& bf, const Shapes& s, const void
     {
       const bool tap = taps && taps->mrf0;
       QVC_PROPAGATE(run_mrf(c, cb, R0, C_UP0, L_RES, bf.x1R, bf.x1O, bf.t1O, bf.xaR, bf.xaO, bf.sum1R,
-                            tens(bf.uO, (int64_t)R0 * C_UP0, C_UP0), 0.1f, tap ? bf.xaR : nullptr));
+                            tens(bf.uO, (int64_t)R0 * C_UP0, C_UP0), 0.1f, tap ? bf.xaR[0] : nullptr));
       if (tap)
-        QVC_PROPAGATE(from_series_major(bf.xaR, C_UP0, (int64_t)R0 * C_UP0, taps->mrf0 + (size_t)b0 * C_UP0 * R0,
+        QVC_PROPAGATE(from_series_major(bf.xaR[0], C_UP0, (int64_t)R0 * C_UP0, taps->mrf0 + (size_t)b0 * C_UP0 * R0,
                                         cb, C_UP0, R0, false, c.st));
     }
     // ups.1: 5 taps, 4*128 phase-major columns: [5T][512] == [20T][128]
@@ -325,7 +374,7 @@ int run_decoder(const Ctx& whole, const Buffers& bf, const Shapes& s, const void
       qvc_conv_args a = layer_args(c, L_UPS + 1, tens(bf.uO, (int64_t)R0 * C_UP0, C_UP0), cb, R0, R0);
       a.seg[0] = seg(0, UP1 * C_UP1);
       a.seg[0].slope = 0.1f;
-      if (!residual_from_operand(c) || (taps && taps->ups1)) a.seg[0].raw = tens(bf.y1R, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
+      if (!residual_from_operand(c.m) || (taps && taps->ups1)) a.seg[0].raw = tens(bf.y1R, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
       a.seg[0].op = tens(bf.y1O, (int64_t)R0 * UP1 * C_UP1, UP1 * C_UP1);
       QVC_PROPAGATE(run(c, a));
       if (taps && taps->ups1)
@@ -338,9 +387,9 @@ int run_decoder(const Ctx& whole, const Buffers& bf, const Shapes& s, const void
       const bool tap = taps && taps->mrf1;
       qvc_tensor fo = tens(reinterpret_cast<char*>(bf.pO) + (size_t)C_UP1 * E, (int64_t)RP * C_UP1, C_UP1);
       QVC_PROPAGATE(run_mrf(c, cb, R1, C_UP1, L_RES + 18, bf.y1R, bf.y1O, bf.t2O, bf.yaR, bf.yaO, bf.sum2R,
-                            fo, 0.01f, tap ? bf.yaR : nullptr));
+                            fo, 0.01f, tap ? bf.yaR[0] : nullptr));
       if (tap)
-        QVC_PROPAGATE(from_series_major(bf.yaR, C_UP1, (int64_t)R1 * C_UP1, taps->mrf1 + (size_t)b0 * C_UP1 * R1,
+        QVC_PROPAGATE(from_series_major(bf.yaR[0], C_UP1, (int64_t)R1 * C_UP1, taps->mrf1 + (size_t)b0 * C_UP1 * R1,
                                         cb, C_UP1, R1, false, c.st));
       QVC_PROPAGATE(reflect_row(bf.pO, (int64_t)RP * C_UP1 * E, (int)(C_UP1 * E), cb, c.st));
     }
@@ -480,55 +529,79 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
     if (spk_sms > 64) spk_sms = 64;
   }
 
-  // prior encoder enc_p (models.py:75-95)
-  {
-    Reserve reserve(spk_sms);
-    qvc_conv_args a = layer_args(c, L_ENC_PRE, tens(bf.unitO, (int64_t)T * UNIT_CH, UNIT_CH), B, T, T);
-    a.seg[0] = seg(0, HID);
-    a.seg[0].raw = tens(bf.xR, bs, HID);
-    a.seg[0].op = tens(bf.xO, bs, HID);
-    QVC_PROPAGATE(run(c, a));
-    // The encoder needs ~0.5 ms (three layers of 128 steps at ~1 us); a WN layer takes ~0.1 ms per 32000 frames of
-    // batch.  Only the layers that can overlap it give up its SMs; the rest of the stack uses the whole machine
-    // (a grid launched while the encoder still holds SMs just has its last CTAs start late).
-    const int64_t frames = (int64_t)B * T;
-    int64_t res_layers = spk_sms ? (160000 + frames - 1) / frames : 0;
-    if (res_layers > 16) res_layers = 16;
-    QVC_PROPAGATE(run_wn(c, bf, B, T, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0, (int)res_layers, spk_sms));
-    tc_reserve_sms(res_layers >= 16 ? spk_sms : 0);
-    qvc_conv_args p = layer_args(c, L_ENC_PROJ, tens(bf.skipO, bs, HID), B, T, T);
-    p.epilogue = QVC_EPI_SAMPLE;
-    p.noise = tens(bf.noiseT, bs, HID);
-    p.seg[0] = seg(0, HID);
-    p.seg[0].raw = tens(bf.zR, bs, HID);
-    p.seg[0].op = tens(bf.zO, bs, HID);
-    if (taps && taps->m_p) p.aux0 = tens(bf.tapA, bs, HID);
-    if (taps && taps->logs_p) p.aux1 = tens(bf.tapB, bs, HID);
-    QVC_PROPAGATE(run(c, p));
-    if (taps && taps->m_p) QVC_PROPAGATE(from_series_major(bf.tapA, HID, bs, taps->m_p, B, HID, T, false, c.st));
-    if (taps && taps->logs_p) QVC_PROPAGATE(from_series_major(bf.tapB, HID, bs, taps->logs_p, B, HID, T, false, c.st));
-    if (taps && taps->z_p) QVC_PROPAGATE(from_series_major(bf.zR, HID, bs, taps->z_p, B, HID, T, false, c.st));
-  }
+  // The prior encoder and the flow run per CHUNK of utterances (wn_chunk_utts): the fp32 residual / skip streams and the
+  // operand copies of a chunk (~0.8 MB per 10 s utterance and tensor) then stay in the 126 MB L2 from one WN layer to
+  // the next instead of round-tripping HBM 32 times per step.  Utterances are independent, so the arithmetic of an
+  // utterance does not depend on the chunking.
+  const int wcb = wn_chunk_utts(B, T);
+  for (int b0 = 0; b0 < B; b0 += wcb) {
+    const int Bc = B - b0 < wcb ? B - b0 : wcb;
+    const size_t o1 = (size_t)b0 * T;                       // frames before this chunk
+    Ctx cc = c;
+    if (cc.lengths) cc.lengths += b0;
+    Buffers cf = bf;
+    const size_t E = c.E;
+    cf.unitO = (char*)bf.unitO + o1 * UNIT_CH * E;
+    cf.xO = (char*)bf.xO + o1 * HID * E;     cf.xO2 = (char*)bf.xO2 + o1 * HID * E;
+    cf.actsO = (char*)bf.actsO + o1 * HID * E;
+    cf.skipO = (char*)bf.skipO + o1 * HID * E; cf.zO = (char*)bf.zO + o1 * HID * E;
+    cf.noiseT = bf.noiseT + o1 * HID;        cf.xR = bf.xR + o1 * HID;
+    cf.skipR = bf.skipR + o1 * HID;          cf.zR = bf.zR + o1 * HID;
+    cf.tapA = bf.tapA + o1 * HID;            cf.tapB = bf.tapB + o1 * HID;
+    const bool first = b0 == 0;
 
-  // flow, reverse direction, Flips folded into the weights (models.py:39-51, modules.py:165-224)
-  if (side) QVC_CHECK_CUDA(cudaStreamWaitEvent(c.st, side->join, 0));      // conditioning vectors ready
-  for (int cpl = 0; cpl < 4; ++cpl) {
-    const int lb = L_FLOW + 10 * cpl;
-    qvc_conv_args a = layer_args(c, lb, tens(bf.zO, bs, HID), B, T, T);
-    a.seg[0] = seg(0, HID);
-    a.seg[0].raw = tens(bf.xR, bs, HID);
-    a.seg[0].op = tens(bf.xO, bs, HID);
-    QVC_PROPAGATE(run(c, a));
-    QVC_PROPAGATE(run_wn(c, bf, B, T, lb + 1, lb + 5, 4, bf.condvec + cpl * 4 * 2 * HID, cond_bs, 2 * HID));
-    qvc_conv_args p = layer_args(c, lb + 9, tens(bf.skipO, bs, HID), B, T, T);
-    p.seg[0] = seg(0, HID);
-    p.seg[0].alpha = -1.f;                          // x1 - m (modules.py:217)
-    p.seg[0].res = tens(bf.zR, bs, HID);
-    p.seg[0].raw = tens(bf.zR, bs, HID);
-    p.seg[0].op = tens(bf.zO, bs, HID);
-    QVC_PROPAGATE(run(c, p));
-    if (taps && taps->flow[cpl])
-      QVC_PROPAGATE(from_series_major(bf.zR, HID, bs, taps->flow[cpl], B, HID, T, (cpl & 1) == 0, c.st));
+    // prior encoder enc_p (models.py:75-95)
+    {
+      Reserve reserve(first ? spk_sms : 0);
+      qvc_conv_args a = layer_args(cc, L_ENC_PRE, tens(cf.unitO, (int64_t)T * UNIT_CH, UNIT_CH), Bc, T, T);
+      a.seg[0] = seg(0, HID);
+      a.seg[0].raw = tens(cf.xR, bs, HID);
+      a.seg[0].op = tens(cf.xO, bs, HID);
+      QVC_PROPAGATE(run(cc, a));
+      // The encoder needs ~0.5 ms (three layers of 128 steps at ~1 us); a WN layer takes ~0.1 ms per 32000 frames of
+      // batch.  Only the layers that can overlap it give up its SMs; the rest of the stack uses the whole machine
+      // (a grid launched while the encoder still holds SMs just has its last CTAs start late).
+      const int64_t frames = (int64_t)Bc * T;
+      int64_t res_layers = (first && spk_sms) ? (160000 + frames - 1) / frames : 0;
+      if (res_layers > 16) res_layers = 16;
+      QVC_PROPAGATE(run_wn(cc, cf, Bc, T, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0, (int)res_layers, spk_sms));
+      tc_reserve_sms(res_layers >= 16 ? spk_sms : 0);
+      qvc_conv_args p = layer_args(cc, L_ENC_PROJ, tens(cf.skipO, bs, HID), Bc, T, T);
+      p.epilogue = QVC_EPI_SAMPLE;
+      p.noise = tens(cf.noiseT, bs, HID);
+      p.seg[0] = seg(0, HID);
+      p.seg[0].raw = tens(cf.zR, bs, HID);
+      p.seg[0].op = tens(cf.zO, bs, HID);
+      if (taps && taps->m_p) p.aux0 = tens(cf.tapA, bs, HID);
+      if (taps && taps->logs_p) p.aux1 = tens(cf.tapB, bs, HID);
+      QVC_PROPAGATE(run(cc, p));
+      const size_t ot = (size_t)b0 * HID * T;
+      if (taps && taps->m_p) QVC_PROPAGATE(from_series_major(cf.tapA, HID, bs, taps->m_p + ot, Bc, HID, T, false, c.st));
+      if (taps && taps->logs_p) QVC_PROPAGATE(from_series_major(cf.tapB, HID, bs, taps->logs_p + ot, Bc, HID, T, false, c.st));
+      if (taps && taps->z_p) QVC_PROPAGATE(from_series_major(cf.zR, HID, bs, taps->z_p + ot, Bc, HID, T, false, c.st));
+    }
+
+    // flow, reverse direction, Flips folded into the weights (models.py:39-51, modules.py:165-224)
+    if (side && first) QVC_CHECK_CUDA(cudaStreamWaitEvent(c.st, side->join, 0));      // conditioning vectors ready
+    const float* cond_c = bf.condvec + (n_embed > 1 ? (int64_t)b0 * m->cond_rows : 0);
+    for (int cpl = 0; cpl < 4; ++cpl) {
+      const int lb = L_FLOW + 10 * cpl;
+      qvc_conv_args a = layer_args(cc, lb, tens(cf.zO, bs, HID), Bc, T, T);
+      a.seg[0] = seg(0, HID);
+      a.seg[0].raw = tens(cf.xR, bs, HID);
+      a.seg[0].op = tens(cf.xO, bs, HID);
+      QVC_PROPAGATE(run(cc, a));
+      QVC_PROPAGATE(run_wn(cc, cf, Bc, T, lb + 1, lb + 5, 4, cond_c + cpl * 4 * 2 * HID, cond_bs, 2 * HID));
+      qvc_conv_args p = layer_args(cc, lb + 9, tens(cf.skipO, bs, HID), Bc, T, T);
+      p.seg[0] = seg(0, HID);
+      p.seg[0].alpha = -1.f;                          // x1 - m (modules.py:217)
+      p.seg[0].res = tens(cf.zR, bs, HID);
+      p.seg[0].raw = tens(cf.zR, bs, HID);
+      p.seg[0].op = tens(cf.zO, bs, HID);
+      QVC_PROPAGATE(run(cc, p));
+      if (taps && taps->flow[cpl])
+        QVC_PROPAGATE(from_series_major(cf.zR, HID, bs, taps->flow[cpl] + (size_t)b0 * HID * T, Bc, HID, T, (cpl & 1) == 0, c.st));
+    }
   }
 
   return run_decoder(c, bf, s, bf.zO, bf.condvec, wave, taps);

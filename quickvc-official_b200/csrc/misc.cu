@@ -171,6 +171,23 @@ extern "C" int qvc_conv1d(const qvc_conv_args* a, qvc_stream_t stream) {
   return QVC_ERR_ARG;
 }
 
+extern "C" int qvc_conv1d_sum(const qvc_conv_args* const* srcs, int nsrc, qvc_stream_t stream) {
+  QVC_REQUIRE(srcs != nullptr && nsrc >= 1 && nsrc <= QVC_MAX_SUM_SOURCES, "qvc_conv1d_sum: 1 <= nsrc <= %d (got %d)",
+              QVC_MAX_SUM_SOURCES, nsrc);
+  for (int i = 0; i < nsrc; ++i) {
+    const qvc_conv_args* a = srcs[i];
+    QVC_REQUIRE(a != nullptr && a->x.ptr && a->w, "qvc_conv1d_sum: source %d has null x / w", i);
+    QVC_REQUIRE(a->batch >= 0 && a->batch <= 65535, "qvc_conv1d_sum: batch %d out of range", a->batch);
+    QVC_REQUIRE(a->k >= 1 && a->dil >= 1 && a->cin > 0 && a->cout > 0 && a->x_rows >= 0 && a->out_rows >= 0 &&
+                    a->x_rows == a->out_rows && a->cout % 16 == 0,
+                "qvc_conv1d_sum: bad geometry in source %d", i);
+  }
+  if (srcs[0]->backend != QVC_BACKEND_TCGEN05) return QVC_ERR_UNSUPPORTED;
+  QVC_REQUIRE(srcs[0]->opformat != QVC_OPF_F32, "qvc_conv1d_sum: the tcgen05 back end needs TF32, FP16 or BF16 operands");
+  if (srcs[0]->batch == 0 || srcs[0]->out_rows == 0) return QVC_OK;
+  return launch_conv_tc_sum(srcs, nsrc, (cudaStream_t)stream);
+}
+
 extern "C" const char* qvc_last_error(void) { return g_err; }
 extern "C" int qvc_abi_version(void) { return QVC_ABI_VERSION; }
 extern "C" uint64_t qvc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

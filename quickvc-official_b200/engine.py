@@ -9,7 +9,7 @@ from typing import Dict, Optional, Tuple
 import torch
 from torch import Tensor
 
-from . import capi, fold
+from . import capi
 
 _PRECISIONS = {"fp32": capi.OPF_F32, "tf32": capi.OPF_TF32, "bf16": capi.OPF_BF16, "fp16": capi.OPF_F16}
 _BACKENDS = {"fma": capi.BACKEND_FMA, "tcgen05": capi.BACKEND_TCGEN05}
@@ -31,7 +31,7 @@ class InferEngine:
     def __init__(self, module: torch.nn.Module, precision: str, backend: Optional[str], chunk_utts: int) -> None:
         # not an nn.Module attribute: keep the module out of our own __dict__ cycle-free via object.__setattr__
         object.__setattr__(self, "_module", module)
-        self._folded: Optional[fold.Folded] = None
+        self._folded = None                                       # (device block, host tail coefficients) behind _model
         self._model: Optional[capi.Model] = None
         self._device: Optional[torch.device] = None
         self._ws: Dict[Tuple[torch.device, int], Tensor] = {}     # one workspace per (device, stream)
@@ -81,14 +81,24 @@ class InferEngine:
                 if v.device != device:
                     raise capi.QvcError(f"parameter {k} lives on {v.device}, inputs on {device}")
             opf = _PRECISIONS[self.precision]
-            # The fold is host arithmetic (fp64, once per load): the device only ever runs this library's own kernels.
-            # The folded tensors are then uploaded on the current stream and that stream is synchronised once, so any
-            # other stream may use the model struct afterwards without an ordering of its own.
+            # The fold is host arithmetic (fp64, once per load) inside the library (qvc_prepare_weights, csrc/fold.cu): the
+            # device only ever runs this library's own kernels.  The folded block is uploaded on the current stream, which
+            # the call synchronises, so any other stream may use the model struct afterwards without an ordering of its own.
             self._watch = list(sd.values())
             self._versions = self._param_versions()
-            self._folded = fold.fold_state_dict({k: v.detach().cpu() for k, v in sd.items()}, opf).to(device)
-            torch.cuda.current_stream(device).synchronize()
-            self._model = fold.build_model_struct(self._folded, opf, _BACKENDS[self.backend], self.chunk_utts)
+            entries, keep = capi.state_entries(sd)
+            nbytes = int(lib.qvc_prepared_bytes(opf))
+            block = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            tail_host = torch.zeros(16 + 272, dtype=torch.float32)
+            model = capi.Model()
+            with torch.cuda.device(device):
+                capi.check(lib.qvc_prepare_weights(entries, len(entries), opf, _BACKENDS[self.backend], block.data_ptr(), nbytes,
+                                                   tail_host.data_ptr(), C.byref(model), self._stream(device)),
+                           "qvc_prepare_weights")
+            del keep
+            model.chunk_utts = self.chunk_utts
+            self._folded = (block, tail_host)            # what the pointers in `model` refer to
+            self._model = model
             self._device = device
         return self._model
 

@@ -331,3 +331,88 @@ def test_frame_paired_convolution_with_tap_hints(opf, k, batch, rows):
     want = ref_conv(x, w, k, 1, pad, rows) + bias.double() + res.double()
     assert float((hint_raw.double() - want).abs().max()) < _tol(opf)
     assert float((hint_raw - plain_raw).abs().max()) < _tol(opf)                    # summation order only
+
+
+# ------------------------------------------------------------------------------------------------
+# qvc_conv1d_sum: a sum of convolutions accumulated in tensor memory with one multi-residual epilogue
+# (the mean of the three ResBlocks of an MRF stage, models.py:378-384)
+# ------------------------------------------------------------------------------------------------
+def _sum_case(opf, B, rows, ch, ks, res_mode, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    srcs = []
+    for k in ks:
+        x = to_op(torch.randn(B, rows, ch, generator=g), opf).to(DEV)
+        w = to_op(torch.randn(ch, k, ch, generator=g) / (ch * k) ** 0.5, opf).to(DEV)
+        bias = torch.randn(ch, generator=g).to(DEV)
+        r = torch.randn(B, rows, ch, generator=g)
+        r_op = to_op(torch.where(r > 0, r, 0.1 * r), opf).to(DEV)
+        srcs.append(dict(x=x, w=w, bias=bias, k=k, res=r.to(DEV), res_op=r_op))
+    return srcs
+
+
+def _run_sum(srcs, opf, rows, ch, res_mode, raw, op):
+    lib = capi.load()
+    args = []
+    for i, s in enumerate(srcs):
+        seg = dict(col0=0, ncols=ch)
+        if res_mode == "res":
+            seg["res"] = s["res"]
+        elif res_mode == "res_op":
+            seg["res_op"], seg["res_inv_slope"] = s["res_op"], 10.0
+        if i == 0:
+            seg.update(beta=1.0 / 3, slope=0.01, raw=raw, op=op)
+        args.append(make_args(s["x"], s["w"], s["bias"], k=s["k"], dil=1, pad_left=(s["k"] - 1) // 2, out_rows=rows, opf=opf,
+                              backend=capi.BACKEND_TCGEN05, segs=[seg]))
+    arr = (C.POINTER(capi.ConvArgs) * len(args))(*[C.pointer(a) for a in args])
+    capi.check(lib.qvc_conv1d_sum(arr, len(args), stream()), "qvc_conv1d_sum")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16, capi.OPF_F16], ids=["tf32", "bf16", "f16"])
+@pytest.mark.parametrize("res_mode", ["res", "res_op", "none"])
+@pytest.mark.parametrize("geom", [(2, 300, 128, (3, 7, 11)), (9, 700, 256, (3, 7, 11)), (1, 37, 256, (11, 3)), (3, 129, 128, (7,))],
+                         ids=["128ch", "256ch-pairs", "two-sources-short", "one-source"])
+def test_conv_sum_matches_reference(opf, res_mode, geom, monkeypatch):
+    B, rows, ch, ks = geom
+    srcs = _sum_case(opf, B, rows, ch, ks, res_mode, 17)
+    want = torch.zeros(B, rows, ch, dtype=torch.float64)
+    for s in srcs:
+        want += ref_conv(s["x"].cpu().float(), s["w"].cpu().float(), s["k"], 1, (s["k"] - 1) // 2, rows) + s["bias"].cpu().double()
+        if res_mode == "res":
+            want += s["res"].cpu().double()
+        elif res_mode == "res_op":
+            rq = s["res_op"].cpu().double()
+            want += torch.where(rq > 0, rq, rq * 10.0)
+    want = want / 3
+    results = []
+    for force in ("0", "1"):                       # one-CTA kernel, then (where the shape allows) the CTA-pair kernel
+        monkeypatch.setenv("QVC_TC_2CTA_FORCE", force)
+        monkeypatch.setenv("QVC_TC_2CTA", force)
+        raw = torch.full((B, rows, ch), float("nan"), device=DEV)
+        op = torch.zeros(B, rows, ch, device=DEV, dtype=op_dtype(opf))
+        _run_sum(srcs, opf, rows, ch, res_mode, raw, op)
+        scale = float(want.abs().max())
+        assert float((raw.cpu().double() - want).abs().max()) < _tol(opf) * scale
+        want_op = torch.where(want > 0, want, want * 0.01)
+        assert float((op.cpu().double() - want_op).abs().max()) < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11)) * scale
+        results.append((raw.clone(), op.clone()))
+    # the two kernels accumulate the same K blocks in the same order: bit-identical (an utterance's samples must not
+    # depend on which kernel its batch size selects)
+    assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
+
+
+def test_conv_sum_rejects_mismatched_sources():
+    opf = capi.OPF_TF32
+    a = _sum_case(opf, 1, 64, 128, (3, 7), "res", 1)
+    b = _sum_case(opf, 1, 64, 256, (3,), "res", 2)
+    raw = torch.zeros(1, 64, 128, device=DEV)
+    with pytest.raises(capi.QvcError):
+        _run_sum([a[0], b[0]], opf, 64, 128, "res", raw, None)
+    with pytest.raises(capi.QvcError):               # mixed residual kinds
+        lib = capi.load()
+        a0 = make_args(a[0]["x"], a[0]["w"], a[0]["bias"], k=3, dil=1, pad_left=1, out_rows=64, opf=opf, backend=capi.BACKEND_TCGEN05,
+                       segs=[dict(col0=0, ncols=128, res=a[0]["res"], raw=raw)])
+        a1 = make_args(a[1]["x"], a[1]["w"], a[1]["bias"], k=7, dil=1, pad_left=3, out_rows=64, opf=opf, backend=capi.BACKEND_TCGEN05,
+                       segs=[dict(col0=0, ncols=128, res_op=a[1]["res_op"], res_inv_slope=10.0)])
+        arr = (C.POINTER(capi.ConvArgs) * 2)(C.pointer(a0), C.pointer(a1))
+        capi.check(lib.qvc_conv1d_sum(arr, 2, stream()), "qvc_conv1d_sum")

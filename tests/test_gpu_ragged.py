@@ -109,3 +109,44 @@ def test_lengths_argument_checks(sd, model_cfg):
     full = net.infer(unit, mel, noise=noise)
     same = net.infer(unit, mel, noise=noise, lengths=torch.tensor([16, 16]))
     assert torch.equal(full, same)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_dead_tiles_are_skipped_without_reading_stale_memory(sd, model_cfg, precision):
+    """Tiles wholly past an utterance's end are skipped by every warp role (DEAD_MARGIN, csrc/common.cuh), so their rows of
+    the workspace keep whatever an earlier call left there.  Poison the workspace with NaN bit patterns first: nothing of
+    it may reach a live sample, and the step must get cheaper than the dense one."""
+    net = _net(sd, model_cfg, precision)
+    T, B = 640, 24
+    lens = [T, 40, 300, 33, 257, 1, 512, 129] * 3
+    unit, mel, noise = _ragged_inputs(B, T, lens, 9)
+    lens_t = torch.tensor(lens)
+    net.infer(unit, mel, noise=noise, lengths=lens_t)                       # sizes the workspace
+    for ws in net._engine._ws.values():
+        ws.fill_(0xFF)                                                      # every fp32 / 16-bit word a NaN
+    wave = net.infer(unit, mel, noise=noise, lengths=lens_t)
+    assert bool(torch.isfinite(wave).all())
+    for b in (0, 1, 2, 3, 4, 5, 6, 7, 23):
+        n = lens[b]
+        alone = net.infer(unit[b:b + 1, :, :n].contiguous(), mel, noise=noise[b:b + 1, :, :n].contiguous())
+        diff = float((wave[b, 0, :320 * n] - alone[0, 0]).abs().max())
+        assert diff <= 2e-6, f"utterance {b} (len {n}) differs from its single call by {diff}"
+        if n < T:
+            assert float(wave[b, 0, 320 * n:].abs().max()) == 0.0
+
+    def ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    dense = ms(lambda: net.infer(unit, mel, noise=noise))
+    ragged = ms(lambda: net.infer(unit, mel, noise=noise, lengths=lens_t))
+    live = sum(lens) / (B * T)
+    print(f"{precision}: dense {dense:.3f} ms, ragged {ragged:.3f} ms, live fraction {live:.2f}")
+    assert ragged < dense * 0.9          # dead tiles cost nothing; the live ones of the longest utterances set the critical path
