@@ -264,19 +264,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
             const int left = min(col_end - col, p.ep.out_rows - (t0 + col));
             return left < 64 ? left : 64;
           };
+          // Two experiments on the residual loads of the 16-bit modes, both dropped (profiles/r02_summary.md): (1) both
+          // 64-frame superblocks of a warp in ONE 128-deep burst, two values per register: c2 layers 25-35 % SLOWER (with
+          // 227 KB of the SM carved out as shared memory almost no L1 is left to hold that many loads in flight);
+          // (2) the residual staged through shared memory by cp.async one superblock ahead (no exposed load latency at
+          // all): no change.
           float r[64];
-          bool primed = false, packed = false;
+          bool primed = false;
           if (warp_live) {
             const int nv = frames_at(col_begin);
-            if constexpr (opf_is16(OPF)) {
-              // 16-bit operand-copy residual, 128 whole frames: both superblocks' loads in one burst, before the wait
-              packed = HN == 128 && k.all_ok && k.sg->res_op.present() && p.ep.out_rows - (t0 + col_begin) >= 128;
-            }
-            if (packed) {
-              if constexpr (opf_is16(OPF)) lin_load_packed<OPF>(k, t0 + col_begin, r);
-            } else if (nv > 0) {
-              lin_load<OPF>(k, t0 + col_begin, nv, r);
-            }
+            if (nv > 0) lin_load<OPF>(k, t0 + col_begin, nv, r);
             primed = true;
           }
           mbar_wait(tmem_full + 8 * buf, bph);
@@ -285,8 +282,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
             for (int col = col_begin; col < col_end; col += 64) {
               const int nv = frames_at(col);
               if (nv <= 0) break;
-              if (!packed && !(primed && col == col_begin)) lin_load<OPF>(k, t0 + col, nv, r);
-              lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)col, packed ? (col == col_begin ? 1 : 2) : 0);
+              if (!(primed && col == col_begin)) lin_load<OPF>(k, t0 + col, nv, r);
+              lin_finish<OPF>(k, t0 + col, nv, r, tbase + (uint32_t)col);
             }
           }
         }

@@ -14,6 +14,9 @@ constexpr int CHUNK_M = 128;              // output channels per CTA and MMA (TM
 constexpr int ROW_BYTES = 128;            // one swizzle-128B row = one K block of one frame / filter row
 constexpr int CHUNK_BYTES = CHUNK_M * ROW_BYTES;
 constexpr int MAX_SMEM = 232448;          // 227 KB
+// 8 epilogue warps (two per TMEM lane quarter).  Tried and dropped (profiles/r02_summary.md): 16 epilogue warps on 32-frame
+// superblocks (576 threads, 96 registers each, 50-370 bytes of spills): +5 % step time in tf32, +1.5 % in fp16, +7 % on
+// a fused WN layer.
 constexpr int NTHREADS = 320;
 constexpr int N_EPI_WARPS = 8;
 constexpr int ACC_COLS = 256;             // TMEM columns per accumulator set
@@ -276,34 +279,13 @@ __device__ __forceinline__ void lin_load(const LinCtx& k, int t, int nv, float* 
   }
 }
 
-// 16-bit operand-copy residuals only: BOTH 64-frame superblocks of a warp's 128 frames in one burst, two values per
-// register (low half = frame i, high half = frame 64 + i).  The second superblock's loads are then in flight before the
-// accumulator is complete as well -- measured (profiles/r02_summary.md): its exposed latency was what made the c2 layers
-// of the 16-bit modes ~45 us slower than their c1 twins.  Requires 128 live frames and a live channel in every lane.
 template <int OPF>
-__device__ __forceinline__ void lin_load_packed(const LinCtx& k, int t, float* r) {
-  static_assert(opf_is16(OPF), "packed residual loads are for the 2-byte operand formats");
-  using OT = typename OpType<OPF>::type;
-  const EpiSeg& sg = *k.sg;
-  const uint16_t* rp16 = reinterpret_cast<const uint16_t*>(sg.res_op.at<OT>(k.b, t, k.c));
-  const int ld = sg.res_op.ld;
-#pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    const uint32_t lo = rp16[i * ld], hi = rp16[(64 + i) * ld];
-    r[i] = __uint_as_float(lo | (hi << 16));
-  }
-}
-
-// packed_half: 0 = r holds one value per register (lin_load); 1 / 2 = r was filled by lin_load_packed and this call
-// finishes the first / second superblock (low / high halves)
-template <int OPF>
-__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float* r, uint32_t taddr, int packed_half = 0) {
+__device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float* r, uint32_t taddr) {
   using OT = typename OpType<OPF>::type;
   const EpiSeg& sg = *k.sg;
   const bool res_from_op = sg.res_op.present();
   const bool has_res = sg.res.present() || res_from_op, has_acc = sg.accin.present();
   const float alpha = sg.alpha, beta = sg.beta, slope = sg.slope;
-  const float inv = sg.res_inv_slope;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int th = t + 32 * h, nvh = nv - 32 * h;
@@ -311,21 +293,16 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
     float v[32];
     tmem_ld32(taddr + 32 * h, v);
     tmem_wait();
-    const float* rr = r + 32 * h;
-    // residual of element i: fp32 as loaded, or the operand copy decoded (leaky-relu undone) on the fly
-    auto resv = [&](int i) -> float {
-      float x = rr[i];
-      if (res_from_op) {
-        if constexpr (opf_is16(OPF)) {
-          uint32_t bits = __float_as_uint(x);
-          if (packed_half == 2) bits >>= 16;
-          else if (packed_half == 1) bits &= 0xffffu;
-          x = op16_to_float<OPF>(bits);
-        }
-        x = x > 0.f ? x : x * inv;
+    float* rr = r + 32 * h;
+    if (res_from_op) {                               // decode the operand copy in place: undo the leaky-relu
+      const float inv = sg.res_inv_slope;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = rr[i];
+        if constexpr (opf_is16(OPF)) x = op16_to_float<OPF>(__float_as_uint(x));
+        rr[i] = x > 0.f ? x : x * inv;
       }
-      return x;
-    };
+    }
     if (has_res && has_acc) {
       // both streams (last convolution of MRF blocks 2 and 3): the accumulate-into tensor is loaded late, 8 at a time
       const float* ap = sg.accin.at<float>(k.b, th, k.c);
@@ -336,11 +313,11 @@ __device__ __forceinline__ void lin_finish(const LinCtx& k, int t, int nv, float
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = (k.ok && g + i < nvh) ? ap[(g + i) * ld] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, resv(g + i)), a[i]);
+        for (int i = 0; i < 8; ++i) v[g + i] = fmaf(beta, fmaf(alpha, v[g + i] + k.bias, rr[g + i]), a[i]);
       }
     } else if (has_res) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, resv(i));
+      for (int i = 0; i < 32; ++i) v[i] = beta * fmaf(alpha, v[i] + k.bias, rr[i]);
     } else if (has_acc) {
       const float ab = alpha * beta;
 #pragma unroll

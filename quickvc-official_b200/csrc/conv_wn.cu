@@ -400,7 +400,13 @@ extern "C" int qvc_wn_layer(const qvc_conv_args* gi, const qvc_conv_args* rs, qv
   if (gi->batch == 0 || gi->out_rows == 0) return QVC_OK;
   const int ntb = (gi->out_rows + PN - 1) / PN;
   const int ntiles = gi->batch * ntb;
-  if (ntiles < tc_sm_count() / 4 && !tc_env_int("QVC_TC_2CTA_FORCE", 0)) return QVC_ERR_UNSUPPORTED;   // latency shapes
+  {
+    // latency shapes (few tiles): QVC_WN_MIN_TILES overrides the threshold below which the layer runs as two launches
+    // (measured, profiles/r02_summary.md: the fused layer on a single 5 s clip saves 32 launches but only ~50 us of 1.9 ms:
+    // the dependent MMA chains, not the launch count, set the latency of a clip)
+    const int min_tiles = tc_env_int("QVC_WN_MIN_TILES", tc_sm_count() / 4);
+    if (ntiles < min_tiles && !tc_env_int("QVC_TC_2CTA_FORCE", 0)) return QVC_ERR_UNSUPPORTED;
+  }
   QVC_REQUIRE(gi->bias != nullptr, "qvc_wn_layer: the gate needs a bias vector");
   EncodeTiledFn encode = tc_get_encode();
   if (!encode) return QVC_ERR_UNSUPPORTED;

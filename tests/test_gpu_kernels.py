@@ -72,7 +72,8 @@ def test_conv_linear(geom, be):
 
 
 @pytest.mark.parametrize("be", BACKENDS, ids=IDS)
-@pytest.mark.parametrize("geom", [(2, 300, 128, 128, 3), (1, 700, 256, 256, 7)], ids=["128ch", "256ch-pairs"])
+@pytest.mark.parametrize("geom", [(2, 300, 128, 128, 3), (1, 700, 256, 256, 7), (13, 700, 256, 256, 7), (20, 1100, 512, 256, 3)],
+                         ids=["128ch", "256ch-one-cta", "256ch-pairs-staged", "pairs-staged-two-rounds"])
 def test_conv_residual_from_operand_copy(be, geom):
     """seg.res_op: the residual given as the operand-format copy of leaky_relu(r, 0.1)."""
     _, backend, opf = be
