@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
+      if (lane == 0) mbar_arrive_relaxed(tmem_empty + 8 * buf);
       ++ait;
     }
   }

@@ -308,7 +308,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + 8 * buf);
+      if (lane == 0) mbar_arrive_cluster_relaxed(lead_tmem_empty + 8 * buf);
       ++ait;
     }
   }

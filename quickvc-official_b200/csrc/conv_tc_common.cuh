@@ -150,6 +150,16 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive WITHOUT release semantics: for barriers that only say "my tcgen05.ld reads of this accumulator are done"
+// (completed by tcgen05.wait::ld, ordered by tcgen05.fence::before_thread_sync) and publish no memory.  The release form
+// compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. it waits until every global store of the tile just finished has drained:
+// 15 % of all warp-stall samples of an epilogue-bound layer sat there (profiles/r02_summary.md).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA loads of a CTA pair: data lands in the issuing CTA, the bytes are counted on the barrier at `bar`
 // (a shared::cluster address -- the leader's)
 __device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {

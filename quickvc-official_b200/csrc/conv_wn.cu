@@ -47,7 +47,7 @@ struct alignas(64) WnParams {
   uint32_t slab_stage_bytes;
   int32_t out_rows, batch;
   int32_t debug;                           // timing experiments only (QVC_WN_DEBUG, results are garbage): 1 no gate epilogue body,
-                                           // 2 no res_skip epilogue loads, 4 no res_skip epilogue body, 8 no GEMM 1, 16 no GEMM 2
+                                           // 2 no res_skip epilogue loads, 4 no res_skip epilogue body, 8 no GEMM 1, 16 no GEMM 2, 32 relaxed acts_ready arrive
   const float* gate_bias;                  // [2H] (+ per-utterance stride)
   int64_t gate_bias_bs;
   EpiParams ep;                            // res_skip epilogue (LINEAR, 1 or 2 segments)
@@ -301,7 +301,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
       asm volatile("fence.proxy.async;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_acts_ready);
+      if (lane == 0) {
+        if (p.debug & 32) mbar_arrive_cluster_relaxed(lead_acts_ready);      // timing experiment only: NOT a correct publication
+        else              mbar_arrive_cluster(lead_acts_ready);
+      }
 
       // ---- res_skip epilogue: acc2 -> x += res, skip += skip (LINEAR epilogue of conv_tc on two accumulators) ----
       LinCtx kx[2];
@@ -337,7 +340,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_wn
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_acc2_empty);
+      if (lane == 0) mbar_arrive_cluster_relaxed(lead_acc2_empty);
     }
   }
 
