@@ -349,6 +349,9 @@ const char* qvc_last_error(void);
 int qvc_abi_version(void);
 /* number of kernel launches enqueued by this process through the library (all streams). */
 uint64_t qvc_launch_count(void);
+/* name of the kernel the calling thread launched last through the library ("" before the first launch): lets a test
+ * assert WHICH kernel served a call (e.g. "conv_tcr_kernel" for the frames-on-rows pair kernel). */
+const char* qvc_last_kernel(void);
 /* 0 when device `dev` is an sm_100 part this library has code for. */
 int qvc_check_device(int dev);
 /* Measurement aid (bench.py's roofline): while enabled, every tcgen05 series-convolution launch is

@@ -116,6 +116,7 @@ SYMBOLS = {
     "qvc_last_error": (C.c_char_p, []),
     "qvc_abi_version": (C.c_int, []),
     "qvc_launch_count": (C.c_uint64, []),
+    "qvc_last_kernel": (C.c_char_p, []),
     "qvc_check_device": (C.c_int, [C.c_int]),
     "qvc_profile": (C.c_int, [C.c_int]),
     "qvc_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -169,3 +170,7 @@ def check(status: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().qvc_launch_count())
+
+
+def last_kernel() -> str:
+    return load().qvc_last_kernel().decode()

@@ -18,6 +18,7 @@ namespace qvc {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void note_kernel(const char* name);        // static string: qvc_last_kernel()
 
 #define QVC_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -58,6 +59,7 @@ inline int post_launch(const char* what) {
     return QVC_ERR_CUDA;
   }
   count_launch();
+  note_kernel(what);
   return QVC_OK;
 }
 

@@ -451,6 +451,10 @@ bool tc_prof_next(cudaEvent_t* e0, cudaEvent_t* e1) { return prof_next(e0, e1); 
 // carries the epilogue).  Layers with an even number of 128-channel chunks and long series go to the CTA-pair kernel.
 int launch_conv_tc_any(const qvc_conv_args* const* srcs, int nsrc, bool sum, cudaStream_t stream) {
   const qvc_conv_args& a = *srcs[0];
+  if (!sum && nsrc == 1) {
+    const int st = launch_conv_tcr(a, stream);
+    if (st != QVC_ERR_UNSUPPORTED) return st;
+  }
   {
     const int st = launch_conv_tc2_sum(srcs, nsrc, sum, stream);
     if (st != QVC_ERR_UNSUPPORTED) return st;

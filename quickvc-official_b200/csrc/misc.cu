@@ -19,6 +19,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+thread_local const char* g_last_kernel = "";
+void note_kernel(const char* name) { g_last_kernel = name; }
 
 namespace {
 
@@ -191,6 +193,7 @@ extern "C" int qvc_conv1d_sum(const qvc_conv_args* const* srcs, int nsrc, qvc_st
 extern "C" const char* qvc_last_error(void) { return g_err; }
 extern "C" int qvc_abi_version(void) { return QVC_ABI_VERSION; }
 extern "C" uint64_t qvc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" const char* qvc_last_kernel(void) { return g_last_kernel; }
 
 extern "C" int qvc_check_device(int dev) {
   int n = 0;

@@ -11,9 +11,10 @@ import torch  # noqa: E402
 from gpu_util import make_args, op_dtype, stream, to_op  # noqa: E402
 from quickvc_official_b200 import capi  # noqa: E402
 
+os.environ.setdefault("QVC_WN_FUSED", "1")          # qvc_wn_layer is off by default (the row kernel serves the WN stacks)
 DEV = "cuda:0"
 lib = capi.load()
-for prec, opf in (("tf32", capi.OPF_TF32), ("bf16", capi.OPF_BF16)):
+for prec, opf in (("tf32", capi.OPF_TF32), ("bf16", capi.OPF_BF16), ("fp16", capi.OPF_F16)):
     B, rows, H, k = int(os.environ.get("CB_BATCH", "64")), 500, 192, 5
     g = torch.Generator().manual_seed(1)
     x = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
@@ -38,7 +39,13 @@ for prec, opf in (("tf32", capi.OPF_TF32), ("bf16", capi.OPF_BF16)):
         capi.check(lib.qvc_conv1d(C.byref(a), stream()), "qvc_conv1d")
         capi.check(lib.qvc_conv1d(C.byref(r), stream()), "qvc_conv1d")
 
-    for name, fn in (("fused", fused), ("split", split)):
+    def gate_only():
+        capi.check(lib.qvc_conv1d(C.byref(a), stream()), "qvc_conv1d")
+
+    def rs_only():
+        capi.check(lib.qvc_conv1d(C.byref(r), stream()), "qvc_conv1d")
+
+    for name, fn in (("fused", fused), ("split", split), ("gate", gate_only), ("rs", rs_only)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

@@ -116,9 +116,10 @@ def test_conv_two_segments_wn_res_skip(be):
 
 @pytest.mark.parametrize("opf", [capi.OPF_TF32, capi.OPF_BF16, capi.OPF_F16], ids=["tf32", "bf16", "f16"])
 @pytest.mark.parametrize("last", [False, True], ids=["res_skip", "skip_only"])
-def test_fused_wn_layer_equals_the_two_convolutions(opf, last):
+def test_fused_wn_layer_equals_the_two_convolutions(opf, last, monkeypatch):
     """qvc_wn_layer (one CTA-pair kernel, activations kept in shared memory) against qvc_conv1d(in_layer) +
     qvc_conv1d(res_skip) on the same operands: same arithmetic, so the results must agree to accumulation noise."""
+    monkeypatch.setenv("QVC_WN_FUSED", "1")          # off by default since the frames-on-rows kernel serves the WN stacks
     lib = capi.load()
     B, rows, H, k = 9, 700, 192, 5                  # 9 x 6 pair tiles; the last frame block is ragged (700 = 5*128 + 60)
     g = torch.Generator(device="cpu").manual_seed(11)
@@ -156,6 +157,108 @@ def test_fused_wn_layer_equals_the_two_convolutions(opf, last):
     for name, w, gt in zip(("x", "skip", "x operand"), want, got):
         scale = float(w.abs().max()) + 1e-6
         assert float((w - gt).abs().max()) < tol * scale, name
+
+
+TC_OPFS = [capi.OPF_TF32, capi.OPF_BF16, capi.OPF_F16]
+TC_IDS = ["tf32", "bf16", "f16"]
+
+
+def _force_rows(monkeypatch):
+    monkeypatch.setenv("QVC_TC_ROWS", "7")           # every eligible layer, not only the 192 / 384-column ones
+    monkeypatch.setenv("QVC_TC_2CTA_FORCE", "1")     # ... however few tiles it has
+
+
+@pytest.mark.parametrize("opf", TC_OPFS, ids=TC_IDS)
+@pytest.mark.parametrize("per_utt_bias", [False, True])
+@pytest.mark.parametrize("rows", [129, 300, 700])
+def test_rows_kernel_gate(opf, per_utt_bias, rows, monkeypatch):
+    """WN in_layer + gate on the frames-on-rows pair kernel (conv_tcr.cu): two 96-channel pieces per 256-frame tile."""
+    _force_rows(monkeypatch)
+    B, H, k = 3, 192, 5
+    g = torch.Generator(device="cpu").manual_seed(7 + rows)
+    x = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(2 * H, k, H, generator=g) / (H * k) ** 0.5, opf).to(DEV)
+    bias = torch.randn(B if per_utt_bias else 1, 2 * H, generator=g).to(DEV)
+    op = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+    raw = torch.zeros(B, rows, H, device=DEV)
+    conv1d(x, w, bias, k=k, dil=1, pad_left=2, out_rows=rows, opf=opf, backend=capi.BACKEND_TCGEN05, epilogue=capi.EPI_GATE,
+           segs=[dict(col0=0, ncols=H, op=op, raw=raw)], bias_bstride=2 * H if per_utt_bias else 0)
+    assert capi.last_kernel() == "conv_tcr_kernel"
+    torch.cuda.synchronize()
+    a = ref_conv(x.cpu().float(), w.cpu().float(), k, 1, 2, rows) + bias.cpu().double().reshape(-1, 1, 2 * H)
+    want = torch.tanh(a[..., :H]) * torch.sigmoid(a[..., H:])
+    assert float((raw.cpu().double() - want).abs().max()) < max(_tol(opf), 1e-5)
+    assert float((op.cpu().double() - want).abs().max()) < max(_tol(opf), 1e-5) + 2 ** -8
+
+
+@pytest.mark.parametrize("opf", TC_OPFS, ids=TC_IDS)
+@pytest.mark.parametrize("last", [False, True], ids=["res_skip", "skip_only"])
+@pytest.mark.parametrize("rows", [130, 700])
+def test_rows_kernel_res_skip(opf, last, rows, monkeypatch):
+    """WN res_skip 1x1 with its two-segment epilogue (x += res in place, skip += skip) on the frames-on-rows kernel."""
+    _force_rows(monkeypatch)
+    B, H = 2, 192
+    g = torch.Generator(device="cpu").manual_seed(5 + rows)
+    acts = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
+    cout = H if last else 2 * H
+    w = to_op(torch.randn(cout, 1, H, generator=g) / H ** 0.5, opf).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    x = torch.randn(B, rows, H, generator=g).to(DEV)
+    skip = torch.randn(B, rows, H, generator=g).to(DEV)
+    x0, skip0 = x.clone(), skip.clone()
+    xo = torch.zeros(B, rows, H, device=DEV, dtype=op_dtype(opf))
+    if last:
+        segs = [dict(col0=0, ncols=H, accin=skip, op=xo)]
+    else:
+        segs = [dict(col0=0, ncols=H, res=x, raw=x, op=xo), dict(col0=H, ncols=H, accin=skip, raw=skip)]
+    conv1d(acts, w, bias, k=1, dil=1, pad_left=0, out_rows=rows, opf=opf, backend=capi.BACKEND_TCGEN05, segs=segs)
+    assert capi.last_kernel() == "conv_tcr_kernel"
+    torch.cuda.synchronize()
+    acc = ref_conv(acts.cpu().float(), w.cpu().float(), 1, 1, 0, rows) + bias.cpu().double()
+    tol = _tol(opf) * 4
+    rnd = 2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11
+    if last:
+        want = skip0.cpu().double() + acc
+        assert float((xo.cpu().double() - want).abs().max()) < tol + rnd * float(want.abs().max())
+        assert torch.equal(skip, skip0) and torch.equal(x, x0)
+    else:
+        want_x = x0.cpu().double() + acc[..., :H]
+        assert float((x.cpu().double() - want_x).abs().max()) < tol
+        assert float((skip.cpu().double() - (skip0.cpu().double() + acc[..., H:])).abs().max()) < tol
+        assert float((xo.cpu().double() - want_x).abs().max()) < tol + rnd * float(want_x.abs().max())
+
+
+# (B, rows, cin, cout, k, dil): piece widths 192 (enc_p.pre, flow pre / post), 256, 128, 2 x 256, 5 x 256
+ROW_GEOMS = [(3, 300, 256, 192, 1, 1), (2, 515, 192, 192, 1, 1), (2, 130, 256, 256, 3, 1), (2, 515, 128, 128, 7, 3),
+             (1, 300, 256, 256, 11, 5), (2, 700, 256, 512, 5, 1), (1, 257, 512, 1280, 4, 1)]
+
+
+@pytest.mark.parametrize("geom", ROW_GEOMS, ids=[f"B{g[0]}_R{g[1]}_{g[2]}to{g[3]}_k{g[4]}d{g[5]}" for g in ROW_GEOMS])
+@pytest.mark.parametrize("opf", TC_OPFS, ids=TC_IDS)
+def test_rows_kernel_linear(geom, opf, monkeypatch):
+    """General LINEAR epilogue (alpha, beta, slope, residual, accumulate-into, raw + operand outputs) on the
+    frames-on-rows kernel, for every piece width it tiles outputs with."""
+    _force_rows(monkeypatch)
+    B, rows, cin, cout, k, dil = geom
+    g = torch.Generator(device="cpu").manual_seed(hash(geom) & 0xffff)
+    x = to_op(torch.randn(B, rows, cin, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(cout, k, cin, generator=g) / (cin * k) ** 0.5, opf).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    res = torch.randn(B, rows, cout, generator=g).to(DEV)
+    accin = torch.randn(B, rows, cout, generator=g).to(DEV)
+    raw = torch.full((B, rows, cout), float("nan"), device=DEV)
+    op = torch.zeros(B, rows, cout, device=DEV, dtype=op_dtype(opf))
+    pad_left = (k - 1) * dil // 2
+    conv1d(x, w, bias, k=k, dil=dil, pad_left=pad_left, out_rows=rows, opf=opf, backend=capi.BACKEND_TCGEN05,
+           segs=[dict(col0=0, ncols=cout, alpha=-1.0, beta=1.0 / 3, slope=0.1, res=res, accin=accin, raw=raw, op=op)])
+    assert capi.last_kernel() == "conv_tcr_kernel"
+    torch.cuda.synchronize()
+    acc = ref_conv(x.cpu().float(), w.cpu().float(), k, dil, pad_left, rows)
+    want = accin.cpu().double() + (1.0 / 3) * (-(acc + bias.cpu().double()) + res.cpu().double())
+    scale = float(want.abs().max())
+    assert float((raw.cpu().double() - want).abs().max()) < _tol(opf) * scale
+    want_op = torch.where(want > 0, want, want * 0.1)
+    assert float((op.cpu().double() - want_op).abs().max()) < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11)) * scale
 
 
 @pytest.mark.parametrize("be", BACKENDS, ids=IDS)
