@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QVC_ABI_VERSION 5
+#define QVC_ABI_VERSION 6
 
 typedef struct CUstream_st* qvc_stream_t;   /* == cudaStream_t */
 
@@ -265,6 +265,13 @@ typedef struct {
    * k + 1 of its (tap, input half) blocks.  256 output rows let a CTA pair issue M = 256 MMAs at the full tensor rate
    * where the 128-row form is capped at 2/3 by its shared-memory operand reads. */
   qvc_layer paired[QVC_NUM_LAYERS];
+  /* Deferred skip sum of a WN stack (modules.py:106-112).  The stack's output  sum_i (W_skip_i . acts_i + b_skip_i)  is ONE
+   * 1x1 convolution over the gated activations of its L layers laid side by side along the channel axis:
+   *   wn_skip[s].w :: [192][1][L*192],  w[n][0][i*192 + c] = res_skip_i.w[(i < L-1 ? 192 : 0) + n][c],  bias[n] = sum_i b_skip_i[n]
+   * (s = 0: enc_p.enc, L = 16;  s = 1 + c: coupling c in execution order, L = 4).  The engine then runs only the residual
+   * half of every res_skip layer (rows [0, 192) of layers[...].w, none for the last layer) and the fp32 running skip sum
+   * the reference reads and rewrites in every layer never exists in memory. */
+  qvc_layer wn_skip[5];
   /* speaker conditioning folded to per-utterance bias vectors:
    * cond_w :: [cond_rows][256] fp32, cond_b :: [cond_rows] fp32 where the rows are
    * 4 couplings x (4 layers x 384) gate biases (cond_layer + in_layer bias, modules.py:83-96)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libqvc_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-QVC_ABI_VERSION = 5
+QVC_ABI_VERSION = 6
 QVC_NUM_LAYERS = 114
 
 OPF_F32, OPF_TF32, OPF_BF16, OPF_F16 = 0, 1, 2, 3
@@ -71,7 +71,7 @@ class Layer(C.Structure):
 class Model(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("opformat", C.c_int32), ("backend", C.c_int32),
                 ("chunk_utts", C.c_int32),
-                ("layers", Layer * QVC_NUM_LAYERS), ("paired", Layer * QVC_NUM_LAYERS),
+                ("layers", Layer * QVC_NUM_LAYERS), ("paired", Layer * QVC_NUM_LAYERS), ("wn_skip", Layer * 5),
                 ("cond_w", C.c_void_p), ("cond_b", C.c_void_p), ("cond_rows", C.c_int32), ("_pad", C.c_int32),
                 ("spk", SpkWeights), ("tail", TailWeights)]
 

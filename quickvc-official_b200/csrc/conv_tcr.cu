@@ -38,6 +38,8 @@ struct alignas(64) TcrParams {
   int32_t slab_box_rows, slab_stages, w_stages;
   uint32_t slab_stage_bytes, w_stage_bytes;
   int32_t batch;
+  int32_t live_cache_words;                // shared-memory words of the ragged-batch length cache
+  int32_t bias_words;                      // LINEAR, shared bias: cout words of it are staged in shared memory (0 = not)
   EpiParams ep;
 };
 
@@ -81,24 +83,37 @@ __device__ __forceinline__ void store_op32(typename OpType<OPF>::type* p, const 
   }
 }
 
-// ---- LINEAR epilogue of one 32-column block of one row (same arithmetic as tc::lin_finish) ----
-struct RowSeg {
-  const EpiSeg* sg;
-  int c;                    // channel of the block's first column within the segment
-  bool in;                  // the block lies inside the segment
+// ---- LINEAR epilogue of one row (same arithmetic as tc::lin_finish), 32-column blocks ----
+// One thread's row pointers into the tensors of an epilogue segment, hoisted out of the block loop: indexing the
+// segment array per block costs register-indexed constant loads on the critical path (10 % of the stall samples of a
+// memory-bound layer, profiles/r02_summary.md).
+template <typename OT>
+struct RowPtrs {
+  const float* first;       // the fp32 stream added first: the residual if there is one, else the accumulate-into tensor
+  const float* second;      // the accumulate-into tensor when there is a residual too
+  float* raw;
+  OT* op;
+  float alpha, beta, slope;
+  int col0, ncols;
+  bool has_res;
 };
-__device__ __forceinline__ RowSeg row_seg(const EpiParams& ep, int n) {
-  RowSeg s;
-  s.sg = &ep.seg[(ep.nseg > 1 && n >= ep.seg[1].col0) ? 1 : 0];
-  s.c = n - s.sg->col0;
-  s.in = s.c >= 0 && s.c + 32 <= s.sg->ncols;
-  return s;
+template <typename OT>
+__device__ __forceinline__ void row_ptrs_from(const EpiSeg& sg, int b, int t, RowPtrs<OT>& r) {
+  r.has_res = sg.res.present();
+  const TRef& f = r.has_res ? sg.res : sg.accin;
+  r.first = f.present() ? f.at<float>(b, t, 0) : nullptr;
+  r.second = (r.has_res && sg.accin.present()) ? sg.accin.at<float>(b, t, 0) : nullptr;
+  r.raw = sg.raw.present() ? sg.raw.at<float>(b, t, 0) : nullptr;
+  r.op = sg.op.present() ? sg.op.at<OT>(b, t, 0) : nullptr;
+  r.alpha = sg.alpha; r.beta = sg.beta; r.slope = sg.slope;
+  r.col0 = sg.col0; r.ncols = sg.ncols;
 }
-// the fp32 stream a block adds first: the residual if there is one, else the accumulate-into tensor
-__device__ __forceinline__ void row_lin_load(const RowSeg& s, int b, int t, bool ok, float* r) {
-  const TRef& src = s.sg->res.present() ? s.sg->res : s.sg->accin;
-  if (ok && s.in && src.present()) load_row32(src.at<float>(b, t, s.c), r);
+template <typename OT>
+__device__ __forceinline__ void row_ptrs(const EpiParams& ep, int si, int b, int t, RowPtrs<OT>& r) {
+  if (si) row_ptrs_from<OT>(ep.seg[1], b, t, r);        // two branches: constant offsets into the parameter bank
+  else    row_ptrs_from<OT>(ep.seg[0], b, t, r);
 }
+
 // 16 consecutive TMEM columns of this thread's lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -110,44 +125,45 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 
-// Finishes one 32-column block of one row in two halves of 16 columns (the accumulator is read 16 columns at a time so
-// that three blocks of prefetched residual fit the register file beside it).  All lanes execute the TMEM loads.
+// Finishes the 32-column block starting at output column n (segment channel c) in two halves of 16 columns: the
+// accumulator is read 16 columns at a time so that three blocks of prefetched residual fit the register file beside it.
+// All lanes execute the TMEM loads; `act` = this lane's row is real and the block lies inside the segment.
 template <int OPF>
-__device__ __forceinline__ void row_lin_finish(const EpiParams& ep, const RowSeg& s, int b, int t, int n, bool ok, bool live,
-                                               uint32_t taddr, const float* r) {
-  using OT = typename OpType<OPF>::type;
-  const EpiSeg& sg = *s.sg;
-  const bool act = ok && s.in;
-  const float alpha = sg.alpha, beta = sg.beta, slope = sg.slope;
-  const bool has_res = sg.res.present(), has_acc = sg.accin.present();
+__device__ __forceinline__ void row_lin_finish(const RowPtrs<typename OpType<OPF>::type>& rp, const float* bias, int n, int c,
+                                               bool act, bool live, uint32_t taddr, const float* r) {
+  const float alpha = rp.alpha, beta = rp.beta, slope = rp.slope;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
     tmem_ld16(taddr + 16 * h, v);
-    tmem_wait();
-    if (!act) continue;
-    const float* rr = r + 16 * h;
-    if (ep.bias) {
-      const float4* bp = reinterpret_cast<const float4*>(ep.bias + (int64_t)b * ep.bias_bs + n + 16 * h);
+    float bv[16];
+    if (bias) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 q = __ldg(bp + i);
-        v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+        const float4 q = *reinterpret_cast<const float4*>(bias + n + 16 * h + 4 * i);
+        bv[4 * i] = q.x; bv[4 * i + 1] = q.y; bv[4 * i + 2] = q.z; bv[4 * i + 3] = q.w;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bv[i] = 0.f;
     }
-    if (has_res && has_acc) {
-      const float* ap = sg.accin.at<float>(b, t, s.c + 16 * h);
+    tmem_wait();
+    if (!act) continue;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += bv[i];
+    const float* rr = r + 16 * h;
+    if (rp.second) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         float a[8];
-        ldg256(ap + 8 * g, reinterpret_cast<uint32_t*>(a));
+        ldg256(rp.second + c + 16 * h + 8 * g, reinterpret_cast<uint32_t*>(a));
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 * g + i] = fmaf(beta, fmaf(alpha, v[8 * g + i], rr[8 * g + i]), a[i]);
       }
-    } else if (has_res) {
+    } else if (rp.first && rp.has_res) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = beta * fmaf(alpha, v[i], rr[i]);
-    } else if (has_acc) {
+    } else if (rp.first) {
       const float ab = alpha * beta;
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaf(ab, v[i], rr[i]);
@@ -156,12 +172,12 @@ __device__ __forceinline__ void row_lin_finish(const EpiParams& ep, const RowSeg
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = ab * v[i];
     }
-    if (sg.raw.present()) {
-      float* wp = sg.raw.at<float>(b, t, s.c + 16 * h);
+    if (rp.raw) {
+      float* wp = rp.raw + c + 16 * h;
       stg256(wp, reinterpret_cast<const uint32_t*>(v));
       stg256(wp + 8, reinterpret_cast<const uint32_t*>(v) + 8);
     }
-    if (sg.op.present()) {
+    if (rp.op) {
       if (live) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);      // leaky-relu, slope <= 1
@@ -169,7 +185,7 @@ __device__ __forceinline__ void row_lin_finish(const EpiParams& ep, const RowSeg
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      OT* op = sg.op.at<OT>(b, t, s.c + 16 * h);
+      auto* op = rp.op + c + 16 * h;
       if constexpr (opf_is16(OPF)) {
         uint32_t w[8];
 #pragma unroll
@@ -206,6 +222,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
   const uint32_t tmem_slot = tmem_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   int32_t* live_s = reinterpret_cast<int32_t*>(tmem_slot_ptr + 4);
+  // LINEAR layers with one bias vector for all utterances keep it in shared memory: the streaming epilogue leaves the L1
+  // no room for it (5 % load hit rate), and a bias load that goes to L2 sits on the critical path of every block
+  float* bias_s = reinterpret_cast<float*>(live_s + p.live_cache_words);
+  const bool bias_in_smem = EPI == QVC_EPI_LINEAR && p.bias_words > 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -214,9 +234,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * p.slab_stages + 2 * p.w_stages + 2; ++i) mbar_init(bar0 + 8 * i, 1);
-    // an accumulator set is drained by ONE group of four epilogue warps per CTA (group h <-> set h)
-    mbar_init(tmem_empty, 2 * (N_EPI_WARPS / 2));
-    mbar_init(tmem_empty + 8, 2 * (N_EPI_WARPS / 2));
+    // an accumulator set is drained by all eight epilogue warps of both CTAs (each group of four takes half of the columns)
+    mbar_init(tmem_empty, 2 * N_EPI_WARPS);
+    mbar_init(tmem_empty + 8, 2 * N_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -231,10 +251,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (p.ep.live != nullptr) {
-    load_live_cache(p.ep, p.batch, live_s);
-    __syncthreads();
-  }
+  if (p.ep.live != nullptr) load_live_cache(p.ep, p.batch, live_s);
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.bias_words; i += blockDim.x) bias_s[i] = p.ep.bias[i];
+  if (p.ep.live != nullptr || bias_in_smem) __syncthreads();
   const int n_cchunks = p.cin / KC;
 
   if (warp == 0) {
@@ -310,7 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9 of both CTAs): group h drains accumulator set h =====================
+    // ===================== epilogue (warps 2..9 of both CTAs): group h takes half h of every tile's columns =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
     const uint32_t h = (uint32_t)(warp - 2) >> 2;
     const int row = q * 32 + lane;
@@ -323,34 +343,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       if (tile_dead(p.ep, live_s, b, tb * 2 * TM)) continue;
       const uint32_t buf = ait & 1u, bph = (ait >> 1) & 1u;
       ++ait;
-      if (buf != h) continue;
       const int t = tb * 2 * TM + (int)rank * TM + row;
       const bool ok = t < p.ep.out_rows;
       const bool live = t < live_rows(p.ep, b);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BUF_COLS;
       if constexpr (EPI == QVC_EPI_LINEAR) {
         // The fp32 stream of a block (residual / accumulate-into) is requested TWO blocks ahead of its use, the first two
-        // before the accumulator is even complete: measured (profiles/r02_summary.md), one 128-byte row segment in flight
-        // per thread (32 KB per SM) sustains only ~1.9 TB/s of a memory-bound layer, the latency under load being ~2.5 us.
+        // before the accumulator is even complete.
         const int nblk = p.np >> 5;
         const int nbase = p.n0[piece];
+        const float* bias = p.ep.bias == nullptr ? nullptr : (bias_in_smem ? bias_s : p.ep.bias + (int64_t)b * p.ep.bias_bs);
+        RowPtrs<OT> rp;
+        int seg_idx = -1;
+        // segment of block blk (re-read only when it changes), channel of its first column, inside the segment?
+        auto enter = [&](int blk, int& c, bool& act) {
+          const int n = nbase + 32 * blk;
+          const int si = (p.ep.nseg > 1 && n >= p.ep.seg[1].col0) ? 1 : 0;
+          if (si != seg_idx) { row_ptrs<OT>(p.ep, si, b, t, rp); seg_idx = si; }
+          c = n - rp.col0;
+          act = ok && c >= 0 && c + 32 <= rp.ncols;
+        };
+        auto request = [&](int blk, float* r) {
+          int c; bool act;
+          enter(blk, c, act);
+          if (act && rp.first) load_row32(rp.first + c, r);
+        };
+        const int blk0 = h ? (nblk + 1) >> 1 : 0, blk1 = h ? nblk : (nblk + 1) >> 1;      // this group's blocks
         float r0[32], r1[32], r2[32];
-        RowSeg s0 = row_seg(p.ep, nbase), s1 = row_seg(p.ep, nbase + 32), s2 = s0;
-        row_lin_load(s0, b, t, ok, r0);
-        if (nblk > 1) row_lin_load(s1, b, t, ok, r1);
+        if (blk0 < blk1) request(blk0, r0);
+        if (blk0 + 1 < blk1) request(blk0 + 1, r1);
         mbar_wait(tmem_full + 8 * buf, bph);
         tc_fence_after();
-        auto step = [&](int blk, RowSeg& sc, float* rc, RowSeg& sn, float* rn) {   // finish block blk (stream rc), request blk + 2 into rn
-          if (blk + 2 < nblk) {
-            sn = row_seg(p.ep, nbase + 32 * (blk + 2));
-            row_lin_load(sn, b, t, ok, rn);
-          }
-          row_lin_finish<OPF>(p.ep, sc, b, t, nbase + 32 * blk, ok, live, taddr + 32 * blk, rc);
+        auto step = [&](int blk, float* rc, float* rn) {     // request block blk + 2 into rn, finish block blk (stream rc)
+          if (blk + 2 < blk1) request(blk + 2, rn);
+          int c; bool act;
+          enter(blk, c, act);
+          row_lin_finish<OPF>(rp, bias, nbase + 32 * blk, c, act, live, taddr + 32 * blk, rc);
         };
-        for (int blk = 0; blk < nblk; blk += 3) {
-          step(blk, s0, r0, s2, r2);
-          if (blk + 1 < nblk) step(blk + 1, s1, r1, s0, r0);
-          if (blk + 2 < nblk) step(blk + 2, s2, r2, s1, r1);
+        for (int blk = blk0; blk < blk1; blk += 3) {
+          step(blk, r0, r2);
+          if (blk + 1 < blk1) step(blk + 1, r1, r0);
+          if (blk + 2 < blk1) step(blk + 2, r2, r1);
         }
       } else {
         const int hp = p.np >> 1;                   // gate channels of this piece: columns [0, hp) tanh, [hp, np) sigmoid
@@ -359,14 +392,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         const EpiSeg& sgm = p.ep.seg[0];
         mbar_wait(tmem_full + 8 * buf, bph);
         tc_fence_after();
-        for (int blk = 0; blk < (hp >> 5); ++blk) {
-          float lo[32], hi[32];
-          tmem_ld32(taddr + 32 * blk, lo);
-          tmem_ld32(taddr + hp + 32 * blk, hi);
-          const int n = ch0 + 32 * blk;
-          float bl[32], bh[32];
+        const int nun = hp >> 4;                    // units of 16 gate channels; this group takes half of them
+        const int u0 = h ? (nun + 1) >> 1 : 0, u1 = h ? nun : (nun + 1) >> 1;
+        for (int u = u0; u < u1; ++u) {
+          float lo[16], hi[16];
+          tmem_ld16(taddr + 16 * u, lo);
+          tmem_ld16(taddr + hp + 16 * u, hi);
+          const int n = ch0 + 16 * u;
+          float bl[16], bh[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(gb + n) + i);
             const float4 c = __ldg(reinterpret_cast<const float4*>(gb + p.ep.half + n) + i);
             bl[4 * i] = a.x; bl[4 * i + 1] = a.y; bl[4 * i + 2] = a.z; bl[4 * i + 3] = a.w;
@@ -374,15 +409,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           }
           tmem_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) lo[i] = fast_gate(lo[i] + bl[i], hi[i] + bh[i]);
+          for (int i = 0; i < 16; ++i) lo[i] = fast_gate(lo[i] + bl[i], hi[i] + bh[i]);
           if (ok) {
-            if (sgm.raw.present()) store_row32(sgm.raw.at<float>(b, t, n), lo);
+            if (sgm.raw.present()) {
+              float* wp = sgm.raw.at<float>(b, t, n);
+              stg256(wp, reinterpret_cast<const uint32_t*>(lo));
+              stg256(wp + 8, reinterpret_cast<const uint32_t*>(lo) + 8);
+            }
             if (sgm.op.present()) {
               if (!live) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) lo[i] = 0.f;
+                for (int i = 0; i < 16; ++i) lo[i] = 0.f;
               }
-              store_op32<OPF>(sgm.op.at<OT>(b, t, n), lo);
+              OT* op = sgm.op.at<OT>(b, t, n);
+              if constexpr (opf_is16(OPF)) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = op16_pack2<OPF>(lo[2 * i], lo[2 * i + 1]);
+                stg256(op, w);
+              } else {
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(to_operand<OPF>(lo[i]));
+                stg256(op, w);
+                stg256(op + 8, w + 8);
+              }
             }
           }
         }
@@ -499,6 +550,8 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
       p.wrow[i][1] = p.n0[i] + np / 2;
     }
   }
+  p.live_cache_words = (int32_t)((live_cache_bytes(a) + 15) / 16 * 4);
+  p.bias_words = (!gate && a.bias && a.bias_bstride == 0 && a.cout <= 2048) ? a.cout : 0;
   p.slab_box_rows = (TM + halo + 7) & ~7;
   p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
   p.w_stage_bytes = (uint32_t)(np / 2) * ROW_BYTES;
@@ -507,7 +560,8 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
   size_t smem = 0;
   bool fits = false;
   for (const auto& opt : stage_options) {
-    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256 + live_cache_bytes(a);
+    smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256 + 4 * (size_t)p.live_cache_words +
+           4 * (size_t)p.bias_words;
     if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
   }
   if (!fits) return QVC_ERR_UNSUPPORTED;

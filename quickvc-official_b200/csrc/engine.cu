@@ -41,7 +41,7 @@ struct Shapes { int B, T, n_embed; int cb; };
 
 struct Buffers {
   // whole batch
-  void *unitO, *xO, *xO2, *actsO, *skipO, *zO;
+  void *unitO, *xO, *xO2, *actsO, *skipO, *zO;      // actsO: gated activations of every layer of a WN stack side by side ([frame][L * 192])
   float *noiseT, *xR, *skipR, *zR, *tapA, *tapB, *condvec, *g;
   void* spk_ws; size_t spk_ws_bytes;
   // per decoder sub-batch; [3]: one per ResBlock of an MRF stage (the three blocks' last convolutions run as ONE sum
@@ -62,6 +62,20 @@ int wn_chunk_utts(int B, int T) {
   }();
   (void)T;
   return (env <= 0 || env > B) ? B : env;
+}
+
+// Deferred skip sum (qvc_model.wn_skip, tcgen05 back end): every layer of a WN stack writes its gated activations into its
+// own 192-channel column block of one [frame][L * 192] tensor, runs only the residual half of res_skip, and ONE 1x1
+// convolution over all L * 192 channels produces the stack's output.  The reference's running fp32 skip sum (read and
+// rewritten by every layer, modules.py:108-112) is never stored: -40 % of the traffic of the memory-bound res_skip layers.
+// QVC_WN_DEFER=0 keeps the layer-by-layer form (the FMA back end always does).
+constexpr int WN_MAX_LAYERS = 16;
+bool wn_defer_skip(const qvc_model* m) {
+  static const int env = [] {
+    const char* e = getenv("QVC_WN_DEFER");
+    return e ? atoi(e) : 1;
+  }();
+  return env != 0 && m->backend == QVC_BACKEND_TCGEN05 && m->wn_skip[0].w != nullptr;
 }
 
 int pick_chunk(const qvc_model* m, int B, int T) {
@@ -102,7 +116,7 @@ size_t carve(const qvc_model* m, const Shapes& s, int mel_batch, int mel_frames,
   b->noiseT = (float*)a.take(n1 * HID * 4);
   b->xR = (float*)a.take(n1 * HID * 4);      b->xO = a.take(n1 * HID * E);
   b->xO2 = a.take(n1 * HID * E);             // ping-pong partner of xO (fused WN layers)
-  b->actsO = a.take(n1 * HID * E);
+  b->actsO = a.take(n1 * (wn_defer_skip(m) ? WN_MAX_LAYERS : 1) * HID * E);
   b->skipR = (float*)a.take(n1 * HID * 4);   b->skipO = a.take(n1 * HID * E);
   b->zR = (float*)a.take(n1 * HID * 4);      b->zO = a.take(n1 * HID * E);
   b->tapA = (float*)a.take(n1 * HID * 4);    b->tapB = (float*)a.take(n1 * HID * 4);
@@ -153,8 +167,11 @@ inline qvc_epi_segment seg(int col0, int ncols) {
   return s;
 }
 
+qvc_conv_args layer_args(const Ctx& c, const qvc_layer& L, qvc_tensor x, int batch, int x_rows, int out_rows);
 qvc_conv_args layer_args(const Ctx& c, int li, qvc_tensor x, int batch, int x_rows, int out_rows) {
-  const qvc_layer& L = c.m->layers[li];
+  return layer_args(c, c.m->layers[li], x, batch, x_rows, out_rows);
+}
+qvc_conv_args layer_args(const Ctx& c, const qvc_layer& L, qvc_tensor x, int batch, int x_rows, int out_rows) {
   qvc_conv_args a{};
   a.x = x; a.batch = batch; a.x_rows = x_rows; a.out_rows = out_rows;
   a.cin = L.cin; a.w = L.w; a.bias = L.bias; a.bias_bstride = 0;
@@ -205,9 +222,48 @@ qvc_conv_args paired_args(const Ctx& c, int li, const void* x, int64_t bs, int b
 
 // One WN stack (modules.py:69-114) over the whole batch.  x: operand/raw pair holding the stack
 // input; on return skipO holds the operand copy of the summed skip output.
-int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int l_in, int l_rs, int n_layers,
+int run_wn_deferred(const Ctx& c, const Buffers& bf, int B, int T, int stack, int l_in, int l_rs, int n_layers,
+                    const float* gate_bias, int64_t gate_bias_bs, int gate_bias_layer_stride, int reserved_layers,
+                    int reserved_sms) {
+  const int64_t bs = (int64_t)T * HID;
+  const int ald = n_layers * HID;                       // row pitch of the side-by-side activations
+  const int64_t abs_ = (int64_t)T * ald;
+  const void* x_in = bf.xO;
+  void* x_out = bf.xO2;
+  for (int i = 0; i < n_layers; ++i) {
+    tc_reserve_sms(i < reserved_layers ? reserved_sms : 0);
+    char* acts_i = reinterpret_cast<char*>(bf.actsO) + (size_t)i * HID * c.E;
+    qvc_conv_args a = layer_args(c, l_in + i, tens(x_in, bs, HID), B, T, T);
+    a.epilogue = QVC_EPI_GATE;
+    if (gate_bias) { a.bias = gate_bias + (int64_t)i * gate_bias_layer_stride; a.bias_bstride = gate_bias_bs; }
+    a.seg[0] = seg(0, HID);
+    a.seg[0].op = tens(acts_i, abs_, ald);
+    QVC_PROPAGATE(run(c, a));
+    if (i == n_layers - 1) break;                       // the last layer has no residual half (modules.py:110-112)
+    qvc_conv_args r = layer_args(c, l_rs + i, tens(acts_i, abs_, ald), B, T, T);
+    r.cout = HID;                                       // rows [0, HID) of the filter: the residual half
+    r.seg[0] = seg(0, HID);
+    r.seg[0].res = tens(bf.xR, bs, HID);
+    r.seg[0].raw = tens(bf.xR, bs, HID);
+    r.seg[0].op = tens(x_out, bs, HID);
+    QVC_PROPAGATE(run(c, r));
+    const void* tmp = x_in;
+    x_in = x_out;
+    x_out = const_cast<void*>(tmp);
+  }
+  tc_reserve_sms(n_layers <= reserved_layers ? reserved_sms : 0);
+  qvc_conv_args k = layer_args(c, c.m->wn_skip[stack], tens(bf.actsO, abs_, ald), B, T, T);
+  k.seg[0] = seg(0, HID);
+  k.seg[0].op = tens(bf.skipO, bs, HID);
+  return run(c, k);
+}
+
+int run_wn(const Ctx& c, const Buffers& bf, int B, int T, int stack, int l_in, int l_rs, int n_layers,
            const float* gate_bias, int64_t gate_bias_bs, int gate_bias_layer_stride, int reserved_layers = 0,
            int reserved_sms = 0) {
+  if (wn_defer_skip(c.m) && n_layers <= WN_MAX_LAYERS && c.m->wn_skip[stack].cin == n_layers * HID)
+    return run_wn_deferred(c, bf, B, T, stack, l_in, l_rs, n_layers, gate_bias, gate_bias_bs, gate_bias_layer_stride,
+                           reserved_layers, reserved_sms);
   const int64_t bs = (int64_t)T * HID;
   // the operand copy of x ping-pongs between two buffers: a fused layer (qvc_wn_layer) writes the new x while other
   // tiles of the same launch still read the old one as convolution halo
@@ -543,7 +599,7 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
     const size_t E = c.E;
     cf.unitO = (char*)bf.unitO + o1 * UNIT_CH * E;
     cf.xO = (char*)bf.xO + o1 * HID * E;     cf.xO2 = (char*)bf.xO2 + o1 * HID * E;
-    cf.actsO = (char*)bf.actsO + o1 * HID * E;
+    cf.actsO = (char*)bf.actsO + o1 * (wn_defer_skip(m) ? WN_MAX_LAYERS : 1) * HID * E;
     cf.skipO = (char*)bf.skipO + o1 * HID * E; cf.zO = (char*)bf.zO + o1 * HID * E;
     cf.noiseT = bf.noiseT + o1 * HID;        cf.xR = bf.xR + o1 * HID;
     cf.skipR = bf.skipR + o1 * HID;          cf.zR = bf.zR + o1 * HID;
@@ -564,7 +620,7 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
       const int64_t frames = (int64_t)Bc * T;
       int64_t res_layers = (first && spk_sms) ? (160000 + frames - 1) / frames : 0;
       if (res_layers > 16) res_layers = 16;
-      QVC_PROPAGATE(run_wn(cc, cf, Bc, T, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0, (int)res_layers, spk_sms));
+      QVC_PROPAGATE(run_wn(cc, cf, Bc, T, 0, L_ENC_IN, L_ENC_RS, 16, nullptr, 0, 0, (int)res_layers, spk_sms));
       tc_reserve_sms(res_layers >= 16 ? spk_sms : 0);
       qvc_conv_args p = layer_args(cc, L_ENC_PROJ, tens(cf.skipO, bs, HID), Bc, T, T);
       p.epilogue = QVC_EPI_SAMPLE;
@@ -591,7 +647,7 @@ extern "C" int qvc_infer(const qvc_model* m, const float* unit, const float* mel
       a.seg[0].raw = tens(cf.xR, bs, HID);
       a.seg[0].op = tens(cf.xO, bs, HID);
       QVC_PROPAGATE(run(cc, a));
-      QVC_PROPAGATE(run_wn(cc, cf, Bc, T, lb + 1, lb + 5, 4, cond_c + cpl * 4 * 2 * HID, cond_bs, 2 * HID));
+      QVC_PROPAGATE(run_wn(cc, cf, Bc, T, 1 + cpl, lb + 1, lb + 5, 4, cond_c + cpl * 4 * 2 * HID, cond_bs, 2 * HID));
       qvc_conv_args p = layer_args(cc, lb + 9, tens(cf.skipO, bs, HID), Bc, T, T);
       p.seg[0] = seg(0, HID);
       p.seg[0].alpha = -1.f;                          // x1 - m (modules.py:217)

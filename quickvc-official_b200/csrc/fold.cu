@@ -199,6 +199,26 @@ struct Builder {
     L.cin = cin; L.cout = cout + pad_rows; L.k = k; L.dil = dil; L.pad_left = pad_left;
   }
 
+  // qvc_model.wn_skip[s]: the skip halves of a WN stack's L res_skip layers (1x1, HID inputs each) side by side along
+  // the input-channel axis, biases summed (modules.py:106-112: every layer but the last has 2 HID outputs, the skip
+  // half second; the last layer's HID outputs are all skip)
+  void skip_sum(int s, const std::string& prefix, int L) {
+    Vec f((size_t)HID * L * HID, 0.0), b((size_t)HID, 0.0);
+    for (int i = 0; i < L; ++i) {
+      const int cout = i < L - 1 ? 2 * HID : HID, r0 = cout - HID;
+      const Vec w = weight(st, prefix + std::to_string(i), cout, HID);
+      const Vec bi = bias(st, prefix + std::to_string(i), cout);
+      for (int n = 0; n < HID; ++n) {
+        for (int c = 0; c < HID; ++c) f[(size_t)n * L * HID + (size_t)i * HID + c] = w[(size_t)(r0 + n) * HID + c];
+        b[(size_t)n] += (double)(float)bi[(size_t)(r0 + n)];
+      }
+    }
+    qvc_layer& S = m->wn_skip[s];
+    S.w = put_operand(A, f, opf);
+    S.bias = put_f32(A, b);
+    S.cin = L * HID; S.cout = HID; S.k = 1; S.dil = 1; S.pad_left = 0;
+  }
+
   // Conv1d weight (cout, cin, k) -> [cout][k][cin], 'same' padding
   void plain(const std::string& prefix, int cout, int cin, int k, int dil = 1, bool with_bias = true) {
     const Vec w = weight(st, prefix, cout, (int64_t)cin * k);
@@ -226,6 +246,7 @@ int fold_all(Store& st, Arena& A, qvc_model* m, int opf, int backend, float* win
   for (int i = 0; i < N_WN_ENC; ++i)
     B.plain("enc_p.enc.res_skip_layers." + std::to_string(i), i < N_WN_ENC - 1 ? 2 * HID : HID, HID, 1);
   B.plain("enc_p.proj", 2 * HID, HID, 1);
+  B.skip_sum(0, "enc_p.enc.res_skip_layers.", N_WN_ENC);
 
   // ---- flow in the execution order of reverse=True: flows 6, 4, 2, 0 (models.py:48).  Couplings 6 and 2 see the
   // channel-reversed state (an odd number of Flips before them); the state is kept in its original orientation and the
@@ -254,6 +275,7 @@ int fold_all(Store& st, Arena& A, qvc_model* m, int opf, int backend, float* win
     for (int i = 0; i < N_WN_FLOW; ++i)
       B.plain(p + ".enc.res_skip_layers." + std::to_string(i), i < N_WN_FLOW - 1 ? 2 * HID : HID, HID, 1);
     B.add_layer(std::move(wq), std::move(bq), true, HID, 1, HID, 1, 0);
+    B.skip_sum(1 + c, p + ".enc.res_skip_layers.", N_WN_FLOW);
     const int rows = N_WN_FLOW * 2 * HID, r0 = c * rows;
     const Vec cw = weight(st, p + ".enc.cond_layer", rows, GIN);
     const Vec cb = bias(st, p + ".enc.cond_layer", rows);

@@ -138,6 +138,7 @@ class Folded:
     def __init__(self) -> None:
         self.layers: List[Dict] = []
         self.paired: Dict[int, Dict] = {}        # layer index -> frame-paired form (frame_pair_filter)
+        self.wn_skip: List[Dict] = []            # per WN stack: deferred skip sum (qvc_model.wn_skip)
         self.tensors: Dict[str, Tensor] = {}
 
     def to(self, device) -> "Folded":
@@ -154,7 +155,7 @@ class Folded:
         for name in list(self.tensors):
             if not name.endswith("_host"):
                 self.tensors[name] = mv(self.tensors[name])
-        for L in list(self.layers) + list(self.paired.values()):
+        for L in list(self.layers) + list(self.paired.values()) + list(self.wn_skip):
             L["w"], L["bias"] = mv(L["w"]), mv(L["bias"])
         return self
 
@@ -201,6 +202,20 @@ def fold_state_dict(sd: Mapping[str, Tensor], opformat: int) -> Folded:
         plain(f"enc_p.rs.{i}", f"enc_p.enc.res_skip_layers.{i}")
     plain("enc_p.proj", "enc_p.proj")
 
+    def skip_sum(prefix: str, n_layers: int) -> None:
+        """qvc_model.wn_skip: the skip halves of a stack's res_skip layers side by side along the input channels."""
+        ws, b = [], torch.zeros(HID, dtype=torch.float64, device=dev)
+        for i in range(n_layers):
+            w = _weight(sd, f"{prefix}{i}")[:, :, 0]                  # (2H | H, H)
+            bi = _bias(sd, f"{prefix}{i}", w.shape[0])
+            ws.append(w[-HID:])
+            b = b + bi[-HID:].float().double()
+        w_all = torch.cat(ws, dim=1).reshape(HID, 1, n_layers * HID)
+        f.wn_skip.append(dict(w=to_operand(w_all, opformat).contiguous(), bias=b.float().contiguous(), cin=n_layers * HID,
+                              cout=HID, k=1, dil=1, pad_left=0))
+
+    skip_sum("enc_p.enc.res_skip_layers.", N_WN_ENC)
+
     # ---- flow, execution order of reverse=True: flows 6, 4, 2, 0 (models.py:48) ----
     # The reference applies Flip before each coupling; two flips cancel, so couplings 6 and 2 see the
     # channel-reversed state and couplings 4 and 0 the original one.  We keep the state in the original
@@ -232,6 +247,7 @@ def fold_state_dict(sd: Mapping[str, Tensor], opformat: int) -> Folded:
         for i in range(N_WN_FLOW):
             plain(f"flow.{c}.rs.{i}", f"{p}.enc.res_skip_layers.{i}")
         f.add_layer(f"flow.{c}.post", wq, bq, 1, 0, opformat)
+        skip_sum(f"{p}.enc.res_skip_layers.", N_WN_FLOW)
         rows = slice(c * N_WN_FLOW * 2 * HID, (c + 1) * N_WN_FLOW * 2 * HID)
         cond_w[rows] = _weight(sd, p + ".enc.cond_layer")[:, :, 0]
         cond_b[rows] = _bias(sd, p + ".enc.cond_layer", N_WN_FLOW * 2 * HID) + torch.cat(
@@ -289,6 +305,10 @@ def build_model_struct(f: Folded, opformat: int, backend: int, chunk_utts: int) 
         m.paired[i].w, m.paired[i].bias = L["w"].data_ptr(), L["bias"].data_ptr()
         m.paired[i].cin, m.paired[i].cout = L["cin"], L["cout"]
         m.paired[i].k, m.paired[i].dil, m.paired[i].pad_left = L["k"], L["dil"], L["pad_left"]
+    for i, L in enumerate(f.wn_skip):
+        m.wn_skip[i].w, m.wn_skip[i].bias = L["w"].data_ptr(), L["bias"].data_ptr()
+        m.wn_skip[i].cin, m.wn_skip[i].cout = L["cin"], L["cout"]
+        m.wn_skip[i].k, m.wn_skip[i].dil, m.wn_skip[i].pad_left = L["k"], L["dil"], L["pad_left"]
     t = f.tensors
     m.cond_w, m.cond_b, m.cond_rows = t["cond_w"].data_ptr(), t["cond_b"].data_ptr(), COND_ROWS
     for l in range(3):

@@ -72,7 +72,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(capi.EpiSegment) == 24 + 5 * 24 + 8
     assert ctypes.sizeof(capi.Layer) == 40
     assert ctypes.sizeof(capi.ConvArgs) == 24 + 16 + 24 + 16 + 8 + 2 * 152 + 3 * 24 + 8 + 16 + 32
-    assert ctypes.sizeof(capi.Model) == 16 + 2 * 114 * 40 + 24 + 11 * 8 + 4 * 8
+    assert ctypes.sizeof(capi.Model) == 16 + (2 * 114 + 5) * 40 + 24 + 11 * 8 + 4 * 8
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted")

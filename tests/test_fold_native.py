@@ -62,6 +62,13 @@ def test_native_fold_equals_python_fold(sd, opf):
         got = _view(block, P.w, L["w"].numel(), _DT[opf])
         assert float((got.float() != L["w"].reshape(-1).float()).float().mean()) < 1e-4
         assert torch.equal(_view(block, P.bias, L["bias"].numel(), torch.float32), L["bias"])
+    assert len(f.wn_skip) == 5
+    for i, L in enumerate(f.wn_skip):
+        S = model.wn_skip[i]
+        assert (S.cin, S.cout, S.k, S.dil, S.pad_left) == (L["cin"], L["cout"], 1, 1, 0)
+        got = _view(block, S.w, L["w"].numel(), _DT[opf])
+        assert float((got.float() != L["w"].reshape(-1).float()).float().mean()) < 1e-4, i
+        assert torch.allclose(_view(block, S.bias, 192, torch.float32), L["bias"], rtol=1e-6, atol=1e-7), i
     t = f.tensors
     assert torch.equal(_view(block, model.cond_w, t["cond_w"].numel(), torch.float32), t["cond_w"].reshape(-1))
     assert torch.equal(_view(block, model.cond_b, t["cond_b"].numel(), torch.float32), t["cond_b"])

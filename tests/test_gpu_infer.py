@@ -148,7 +148,7 @@ def test_argument_errors(sd, model_cfg):
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
 def test_pair_kernels_on_the_golden_case(precision, sd, model_cfg, monkeypatch):
-    """The CTA-pair (cta_group::2) convolutions and the fused WN-layer kernel are chosen only for shapes that fill
+    """The CTA-pair (cta_group::2) convolutions -- channel-major and frames-on-rows -- are chosen only for shapes that fill
     the machine; QVC_TC_2CTA_FORCE selects them for the small golden case too, so they are checked per stage
     against the reference's own outputs (not only at full size)."""
     monkeypatch.setenv("QVC_TC_2CTA_FORCE", "1")
@@ -163,13 +163,6 @@ def test_pair_kernels_on_the_golden_case(precision, sd, model_cfg, monkeypatch):
     for n, ref in gold.items():
         assert synth.rel_l2(taps[n], ref) < stage_tol, n
     assert synth.max_abs(wave, gold["wave"]) < wave_tol
-    before = capi.launch_count()
-    net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
-    forced = capi.launch_count() - before
-    monkeypatch.delenv("QVC_TC_2CTA_FORCE")
-    before = capi.launch_count()
-    net.infer(unit.to(DEV), mel.to(DEV), noise=noise.to(DEV))
-    assert capi.launch_count() - before > forced          # the fused WN layers save one launch each
 
 
 @pytest.mark.parametrize("force_pairs", [False, True], ids=["auto", "pairs"])
