@@ -40,6 +40,7 @@ struct alignas(64) TcrParams {
   int32_t batch;
   int32_t live_cache_words;                // shared-memory words of the ragged-batch length cache
   int32_t bias_words;                      // LINEAR, shared bias: cout words of it are staged in shared memory (0 = not)
+  int32_t debug;                           // timing experiments only (QVC_TCR_DEBUG, results are garbage): 1 no epilogue body, 2 no MMAs
   EpiParams ep;
 };
 
@@ -202,7 +203,7 @@ __device__ __forceinline__ void row_lin_finish(const RowPtrs<typename OpType<OPF
   }
 }
 
-template <int OPF, int EPI>
+template <int OPF, int EPI, bool LEAN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tcr_kernel(const __grid_constant__ TcrParams p) {
   constexpr int ESIZE = opf_is16(OPF) ? 2 : 4;
   constexpr int KC = ROW_BYTES / ESIZE;
@@ -314,8 +315,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
             const uint64_t adesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
             const uint64_t bdesc = desc_hi | (uint64_t)(((w0 + ws * p.w_stage_bytes) & 0x3FFFFu) >> 4);
             if (elect_one()) {
+              if (!(p.debug & 2)) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma2<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                for (int ks = 0; ks < 4; ++ks) umma2<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+              }
               tc2_commit(empty_w + 8 * ws);
               if (j == k - 1) tc2_commit(empty_slab + 8 * s);
             }
@@ -348,7 +351,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       const bool live = t < live_rows(p.ep, b);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BUF_COLS;
       if constexpr (EPI == QVC_EPI_LINEAR) {
-        // The fp32 stream of a block (residual / accumulate-into) is requested TWO blocks ahead of its use, the first two
+        // The fp32 stream of a block (residual / accumulate-into) is requested one block ahead of its use, the first one
         // before the accumulator is even complete.
         const int nblk = p.np >> 5;
         const int nbase = p.n0[piece];
@@ -369,21 +372,110 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           if (act && rp.first) load_row32(rp.first + c, r);
         };
         const int blk0 = h ? (nblk + 1) >> 1 : 0, blk1 = h ? nblk : (nblk + 1) >> 1;      // this group's blocks
-        float r0[32], r1[32], r2[32];
+        // ---- lean instance (chosen by the host: every block of a group inside ONE segment, at most one fp32 input stream,
+        // bias shared).  Straight-line code per 16 columns; the generic instance below spends ~15 instructions per element
+        // on predicates, segment look-ups and address arithmetic and is issue-bound on memory-bound layers
+        // (profiles/r02_summary.md); this one ~5.
+        if constexpr (LEAN) {
+          if (blk0 < blk1 && !(p.debug & 1)) {
+            const int n_first = nbase + 32 * blk0;
+            const int si = (p.ep.nseg > 1 && n_first >= p.ep.seg[1].col0) ? 1 : 0;
+            row_ptrs<OT>(p.ep, si, b, t, rp);
+            const float* first = rp.first ? rp.first + (n_first - rp.col0) : nullptr;
+            float* raw = rp.raw ? rp.raw + (n_first - rp.col0) : nullptr;
+            OT* op = rp.op ? rp.op + (n_first - rp.col0) : nullptr;
+            const float* bs = p.ep.bias ? bias_s + n_first : nullptr;
+            const float alpha = rp.alpha, beta = rp.beta, ab = rp.alpha * rp.beta, slope = rp.slope;
+            const bool is_res = rp.has_res, ragged = p.ep.live != nullptr;
+            const int nb = blk1 - blk0;
+            float ra[32], rb[32];
+            if (first && ok) load_row32(first, ra);
+            mbar_wait(tmem_full + 8 * buf, bph);
+            tc_fence_after();
+            auto lean_block = [&](int i, const float* rc, float* rn) {
+              if (first && ok && i + 1 < nb) load_row32(first + 32 * (i + 1), rn);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {               // two halves of 16 columns: keeps the live registers low
+                float v[16];
+                tmem_ld16(taddr + 32 * (blk0 + i) + 16 * hh, v);
+                float4 bq[4];
+                if (bs) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) bq[j] = *reinterpret_cast<const float4*>(bs + 32 * i + 16 * hh + 4 * j);
+                }
+                tmem_wait();
+                if (!ok) continue;
+                if (bs) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    v[4 * j] += bq[j].x; v[4 * j + 1] += bq[j].y; v[4 * j + 2] += bq[j].z; v[4 * j + 3] += bq[j].w;
+                  }
+                }
+                const float* rr = rc + 16 * hh;
+                if (first) {
+                  if (is_res) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = beta * fmaf(alpha, v[j], rr[j]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaf(ab, v[j], rr[j]);
+                  }
+                } else if (ab != 1.f) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] *= ab;
+                }
+                if (raw) {
+                  stg256(raw + 32 * i + 16 * hh, reinterpret_cast<const uint32_t*>(v));
+                  stg256(raw + 32 * i + 16 * hh + 8, reinterpret_cast<const uint32_t*>(v) + 8);
+                }
+                if (op) {
+                  if (slope != 1.f) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+                  }
+                  if (ragged && !live) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                  }
+                  OT* o = op + 32 * i + 16 * hh;
+                  if constexpr (opf_is16(OPF)) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = op16_pack2<OPF>(v[2 * j], v[2 * j + 1]);
+                    stg256(o, w);
+                  } else {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(to_operand<OPF>(v[j]));
+                    stg256(o, w);
+                    stg256(o + 8, w + 8);
+                  }
+                }
+              }
+            };
+            for (int i = 0; i < nb; i += 2) {
+              lean_block(i, ra, rb);
+              if (i + 1 < nb) lean_block(i + 1, rb, ra);
+            }
+          } else {
+            mbar_wait(tmem_full + 8 * buf, bph);
+            tc_fence_after();
+          }
+        } else {
+        float r0[32], r1[32];
         if (blk0 < blk1) request(blk0, r0);
-        if (blk0 + 1 < blk1) request(blk0 + 1, r1);
         mbar_wait(tmem_full + 8 * buf, bph);
         tc_fence_after();
-        auto step = [&](int blk, float* rc, float* rn) {     // request block blk + 2 into rn, finish block blk (stream rc)
-          if (blk + 2 < blk1) request(blk + 2, rn);
+        auto step = [&](int blk, float* rc, float* rn) {     // request block blk + 1 into rn, finish block blk (stream rc)
+          if (blk + 1 < blk1) request(blk + 1, rn);
           int c; bool act;
           enter(blk, c, act);
           row_lin_finish<OPF>(rp, bias, nbase + 32 * blk, c, act, live, taddr + 32 * blk, rc);
         };
-        for (int blk = blk0; blk < blk1; blk += 3) {
-          step(blk, r0, r2);
+        for (int blk = blk0; blk < blk1; blk += 2) {
+          step(blk, r0, r1);
           if (blk + 1 < blk1) step(blk + 1, r1, r0);
-          if (blk + 2 < blk1) step(blk + 2, r2, r1);
+        }
         }
       } else {
         const int hp = p.np >> 1;                   // gate channels of this piece: columns [0, hp) tanh, [hp, np) sigmoid
@@ -456,11 +548,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
   }
 }
 
-template <int OPF, int EPI>
+template <int OPF, int EPI, bool LEAN>
 int launch_r(const TcrParams& p, int grid, size_t smem, cudaStream_t stream) {
   static std::atomic<bool> attr_done[MAX_DEVICES];
   if (first_use_on_device(attr_done))
-    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tcr_kernel<OPF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    QVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tcr_kernel<OPF, EPI, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -474,7 +566,7 @@ int launch_r(const TcrParams& p, int grid, size_t smem, cudaStream_t stream) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = tc_prof_next(&e0, &e1);
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e0, stream));
-  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tcr_kernel<OPF, EPI>, p));
+  QVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tcr_kernel<OPF, EPI, LEAN>, p));
   if (timed) QVC_CHECK_CUDA(cudaEventRecord(e1, stream));
   return post_launch("conv_tcr_kernel");
 }
@@ -550,6 +642,7 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
       p.wrow[i][1] = p.n0[i] + np / 2;
     }
   }
+  p.debug = tc_env_int("QVC_TCR_DEBUG", 0);
   p.live_cache_words = (int32_t)((live_cache_bytes(a) + 15) / 16 * 4);
   p.bias_words = (!gate && a.bias && a.bias_bstride == 0 && a.cout <= 2048) ? a.cout : 0;
   p.slab_box_rows = (TM + halo + 7) & ~7;
@@ -559,7 +652,16 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
   static const int stage_options[][2] = {{4, 8}, {3, 8}, {3, 6}, {2, 6}, {2, 4}, {2, 3}, {2, 2}};
   size_t smem = 0;
   bool fits = false;
+  {
+    const int ss = tc_env_int("QVC_TCR_SS", 0), ws = tc_env_int("QVC_TCR_WS", 0);       // tuning override
+    if (ss >= 1 && ss <= 16 && ws >= 2 && ws <= 16) {
+      smem = (size_t)ss * p.slab_stage_bytes + (size_t)ws * p.w_stage_bytes + 1024 + 256 + 4 * (size_t)p.live_cache_words +
+             4 * (size_t)p.bias_words;
+      if (smem <= (size_t)MAX_SMEM) { p.slab_stages = ss; p.w_stages = ws; fits = true; }
+    }
+  }
   for (const auto& opt : stage_options) {
+    if (fits) break;
     smem = (size_t)opt[0] * p.slab_stage_bytes + (size_t)opt[1] * p.w_stage_bytes + 1024 + 256 + 4 * (size_t)p.live_cache_words +
            4 * (size_t)p.bias_words;
     if (smem <= (size_t)MAX_SMEM) { p.slab_stages = opt[0]; p.w_stages = opt[1]; fits = true; break; }
@@ -589,9 +691,26 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
   }
   int pairs = tc_sm_count() / 2;
   if (ntiles < pairs) pairs = ntiles;
-#define QVC_TCR_DISPATCH(OPF)                                                            \
-  return gate ? launch_r<OPF, QVC_EPI_GATE>(p, 2 * pairs, smem, stream)                  \
-              : launch_r<OPF, QVC_EPI_LINEAR>(p, 2 * pairs, smem, stream);
+  // lean LINEAR instance: every group's column range ([0, ceil(nblk / 2)) and the rest of each piece) lies inside one
+  // segment, no segment has both a residual and an accumulate-into tensor, and the bias (if any) sits in shared memory
+  bool lean = !gate && (a.bias == nullptr || p.bias_words > 0);
+  if (lean) {
+    const int nblk = np / 32, split = (nblk + 1) / 2;
+    for (int i = 0; i < npieces && lean; ++i)
+      for (int hgrp = 0; hgrp < 2 && lean; ++hgrp) {
+        const int c0 = p.n0[i] + 32 * (hgrp ? split : 0), c1 = p.n0[i] + 32 * (hgrp ? nblk : split);
+        if (c0 >= c1) continue;
+        const int si = (a.nseg > 1 && c0 >= a.seg[1].col0) ? 1 : 0;
+        const qvc_epi_segment& g = a.seg[si];
+        if (c0 < g.col0 || c1 > g.col0 + g.ncols || (g.res.ptr && g.accin.ptr)) lean = false;
+        if (si == 0 && a.nseg > 1 && c1 > a.seg[1].col0) lean = false;
+      }
+  }
+  if (tc_env_int("QVC_TCR_LEAN", 1) == 0) lean = false;
+#define QVC_TCR_DISPATCH(OPF)                                                                  \
+  return gate ? launch_r<OPF, QVC_EPI_GATE, false>(p, 2 * pairs, smem, stream)                 \
+              : (lean ? launch_r<OPF, QVC_EPI_LINEAR, true>(p, 2 * pairs, smem, stream)        \
+                      : launch_r<OPF, QVC_EPI_LINEAR, false>(p, 2 * pairs, smem, stream));
   if (a.opformat == QVC_OPF_BF16) { QVC_TCR_DISPATCH(QVC_OPF_BF16) }
   if (a.opformat == QVC_OPF_F16) { QVC_TCR_DISPATCH(QVC_OPF_F16) }
   QVC_TCR_DISPATCH(QVC_OPF_TF32)

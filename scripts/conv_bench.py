@@ -56,7 +56,7 @@ if os.environ.get("CB_DEBUGS"):
     CONFIGS = [dict(QVC_TC_DEBUG=g) for g in os.environ["CB_DEBUGS"].split(",")]
 if os.environ.get("CB_CFGS"):     # e.g. "QVC_TC_XPROM=256;QVC_TC_DEBUG=8,QVC_TC_XPROM=256"
     CONFIGS = [dict(kv.split("=") for kv in c.split(",") if kv) for c in os.environ["CB_CFGS"].split(";")]
-KEYS = ("QVC_TC_XPROM", "QVC_TC_DEBUG", "QVC_TC_SS", "QVC_TC_WS", "QVC_TC_G", "QVC_TC_N", "QVC_TC_GRID")
+KEYS = ("QVC_TCR_DEBUG", "QVC_TCR_SS", "QVC_TCR_WS", "QVC_TC_ROWS", "QVC_TC_XPROM", "QVC_TC_DEBUG", "QVC_TC_SS", "QVC_TC_WS", "QVC_TC_G", "QVC_TC_N", "QVC_TC_GRID")
 
 
 def run_layer(name, rows, cin, cout, k, dil, kind):

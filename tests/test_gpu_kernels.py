@@ -194,9 +194,12 @@ def test_rows_kernel_gate(opf, per_utt_bias, rows, monkeypatch):
 @pytest.mark.parametrize("opf", TC_OPFS, ids=TC_IDS)
 @pytest.mark.parametrize("last", [False, True], ids=["res_skip", "skip_only"])
 @pytest.mark.parametrize("rows", [130, 700])
-def test_rows_kernel_res_skip(opf, last, rows, monkeypatch):
-    """WN res_skip 1x1 with its two-segment epilogue (x += res in place, skip += skip) on the frames-on-rows kernel."""
+@pytest.mark.parametrize("lean", [True, False], ids=["lean", "generic"])
+def test_rows_kernel_res_skip(opf, last, rows, lean, monkeypatch):
+    """WN res_skip 1x1 with its two-segment epilogue (x += res in place, skip += skip) on the frames-on-rows kernel, on
+    its lean epilogue instance (one segment per column group) and on the generic one."""
     _force_rows(monkeypatch)
+    monkeypatch.setenv("QVC_TCR_LEAN", "1" if lean else "0")
     B, H = 2, 192
     g = torch.Generator(device="cpu").manual_seed(5 + rows)
     acts = to_op(torch.randn(B, rows, H, generator=g), opf).to(DEV)
