@@ -593,6 +593,6 @@ int tc_env_int(const char* name, int dflt);
 bool tc_prof_next(cudaEvent_t* e0, cudaEvent_t* e1);
 int launch_conv_tc2(const qvc_conv_args& a, cudaStream_t stream);     // conv_tc2.cu; QVC_ERR_UNSUPPORTED = not applicable
 int launch_conv_tc2_sum(const qvc_conv_args* const* srcs, int nsrc, bool sum, cudaStream_t stream);
-int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream);      // conv_tcr.cu (frames on the accumulator rows); QVC_ERR_UNSUPPORTED = not applicable
+int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream);   // conv_tcr.cu (frames on the accumulator rows); QVC_ERR_UNSUPPORTED = not applicable
 
 }  // namespace qvc

@@ -28,8 +28,9 @@ constexpr int BUF_COLS = 256;             // TMEM columns between the two accumu
 
 struct alignas(64) TcrParams {
   CUtensorMap mx;                          // x as (channel, frame, utterance)
-  CUtensorMap mw;                          // w as (tap*cin + channel, output channel); box = np / 2 rows
+  CUtensorMap mw;                          // w as (channel, output channel, tap); box = one channel chunk x np / 2 rows x tg taps
   int32_t cin, k, dil, pad_left;
+  int32_t tg;                              // taps per filter stage (one TMA operation brings tg taps of one channel chunk)
   int32_t np;                              // accumulator columns per piece (the N of the MMA)
   int32_t npieces;
   int32_t wrow[MAXPIECES][2];              // first filter row CTA r loads for piece p
@@ -92,9 +93,10 @@ template <typename OT>
 struct RowPtrs {
   const float* first;       // the fp32 stream added first: the residual if there is one, else the accumulate-into tensor
   const float* second;      // the accumulate-into tensor when there is a residual too
+  const OT* res_op;         // the residual as an operand-format tensor holding leaky_relu(r) (lean instance only)
   float* raw;
   OT* op;
-  float alpha, beta, slope;
+  float alpha, beta, slope, res_inv_slope;
   int col0, ncols;
   bool has_res;
 };
@@ -104,6 +106,8 @@ __device__ __forceinline__ void row_ptrs_from(const EpiSeg& sg, int b, int t, Ro
   const TRef& f = r.has_res ? sg.res : sg.accin;
   r.first = f.present() ? f.at<float>(b, t, 0) : nullptr;
   r.second = (r.has_res && sg.accin.present()) ? sg.accin.at<float>(b, t, 0) : nullptr;
+  r.res_op = sg.res_op.present() ? sg.res_op.at<OT>(b, t, 0) : nullptr;
+  r.res_inv_slope = sg.res_inv_slope;
   r.raw = sg.raw.present() ? sg.raw.at<float>(b, t, 0) : nullptr;
   r.op = sg.op.present() ? sg.op.at<OT>(b, t, 0) : nullptr;
   r.alpha = sg.alpha; r.beta = sg.beta; r.slope = sg.slope;
@@ -265,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
       const uint32_t lead_full_slab = map_to_cta(full_slab, 0), lead_full_w = map_to_cta(full_w, 0);
       const uint32_t slab_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
-      const int cin = p.cin, k = p.k, pad_left = p.pad_left;
+      const int k = p.k, pad_left = p.pad_left, tg = p.tg;
       uint32_t s = 0, ph = 0, ws = 0, wph = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs) {
         const int piece = tile % p.npieces;
@@ -279,10 +283,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           if (leader) mbar_expect_tx(full_slab + 8 * s, 2 * slab_bytes);
           tma2_load_3d(slab0 + s * p.slab_stage_bytes, &p.mx, lead_full_slab + 8 * s, cc * KC, t0 - pad_left, b);
           if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1u; }
-          for (int j = 0; j < k; ++j) {
+          // One operation per group of tg taps: the single producer thread spends ~400 cycles per TMA operation (wait,
+          // expect_tx, issue), which bounded every layer whose stage feeds fewer than ~400 cycles of MMAs
+          // (profiles/r02_summary.md: a k = 3, 128 -> 128 layer took 61 us with neither MMAs nor epilogue).
+          for (int j = 0; j < k; j += tg) {
             mbar_wait(empty_w + 8 * ws, wph ^ 1u);
             if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * p.w_stage_bytes);
-            tma2_load_2d(w0 + ws * p.w_stage_bytes, &p.mw, lead_full_w + 8 * ws, j * cin + cc * KC, wrow);
+            tma2_load_3d(w0 + ws * p.w_stage_bytes, &p.mw, lead_full_w + 8 * ws, cc * KC, wrow, j);
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -294,7 +301,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
       const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.np >> 3) << 17) |
                              ((uint32_t)((2 * TM) >> 4) << 24);
       const uint64_t desc_hi = smem_desc(0);
-      const int k = p.k, dil = p.dil;
+      const int k = p.k, dil = p.dil, tg = p.tg;
+      const uint32_t w_tap_bytes = (uint32_t)(p.np >> 1) * ROW_BYTES;
       uint32_t s = 0, ph = 0, ws = 0, wph = 0, ait = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs) {
         {
@@ -308,19 +316,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         for (int cc = 0; cc < n_cchunks; ++cc) {
           mbar_wait(full_slab + 8 * s, ph);
           const uint32_t slab = slab0 + s * p.slab_stage_bytes;
-          for (int j = 0; j < k; ++j) {
+          for (int j0 = 0; j0 < k; j0 += tg) {
             mbar_wait(full_w + 8 * ws, wph);
             tc_fence_after();
-            const uint32_t first = (cc | j) == 0 ? 0u : 1u;
-            const uint64_t adesc = desc_hi | (uint64_t)(((slab + (uint32_t)(j * dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
-            const uint64_t bdesc = desc_hi | (uint64_t)(((w0 + ws * p.w_stage_bytes) & 0x3FFFFu) >> 4);
+            const int jn = k - j0 < tg ? k - j0 : tg;
+            const uint64_t adesc0 = desc_hi | (uint64_t)(((slab + (uint32_t)(j0 * dil) * ROW_BYTES) & 0x3FFFFu) >> 4);
+            const uint64_t bdesc0 = desc_hi | (uint64_t)(((w0 + ws * p.w_stage_bytes) & 0x3FFFFu) >> 4);
             if (elect_one()) {
               if (!(p.debug & 2)) {
+                for (int jj = 0; jj < jn; ++jj) {
+                  const uint32_t first = (cc | j0 | jj) == 0 ? 0u : 1u;
+                  const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(jj * dil) * (ROW_BYTES >> 4));
+                  const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)jj * (w_tap_bytes >> 4));
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma2<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                  for (int ks = 0; ks < 4; ++ks) umma2<OPF>(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, ks == 0 ? first : 1u);
+                }
               }
               tc2_commit(empty_w + 8 * ws);
-              if (j == k - 1) tc2_commit(empty_slab + 8 * s);
+              if (j0 + tg >= k) tc2_commit(empty_slab + 8 * s);
             }
             __syncwarp();
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
@@ -382,6 +395,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
             const int si = (p.ep.nseg > 1 && n_first >= p.ep.seg[1].col0) ? 1 : 0;
             row_ptrs<OT>(p.ep, si, b, t, rp);
             const float* first = rp.first ? rp.first + (n_first - rp.col0) : nullptr;
+            const OT* rop = rp.res_op ? rp.res_op + (n_first - rp.col0) : nullptr;
+            const float inv_slope = rp.res_inv_slope;
             float* raw = rp.raw ? rp.raw + (n_first - rp.col0) : nullptr;
             OT* op = rp.op ? rp.op + (n_first - rp.col0) : nullptr;
             const float* bs = p.ep.bias ? bias_s + n_first : nullptr;
@@ -389,11 +404,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
             const bool is_res = rp.has_res, ragged = p.ep.live != nullptr;
             const int nb = blk1 - blk0;
             float ra[32], rb[32];
-            if (first && ok) load_row32(first, ra);
+            // operand-format residual: 32 values = 64 or 128 bytes, kept as raw bits until used
+            auto load_rop = [&](const OT* src, float* dst) {
+              ldg256(src, reinterpret_cast<uint32_t*>(dst));
+              ldg256(reinterpret_cast<const char*>(src) + 32, reinterpret_cast<uint32_t*>(dst) + 8);
+              if constexpr (!opf_is16(OPF)) {
+                ldg256(reinterpret_cast<const char*>(src) + 64, reinterpret_cast<uint32_t*>(dst) + 16);
+                ldg256(reinterpret_cast<const char*>(src) + 96, reinterpret_cast<uint32_t*>(dst) + 24);
+              }
+            };
+            if (ok) {
+              if (first) load_row32(first, ra);
+              else if (rop) load_rop(rop, ra);
+            }
             mbar_wait(tmem_full + 8 * buf, bph);
             tc_fence_after();
             auto lean_block = [&](int i, const float* rc, float* rn) {
-              if (first && ok && i + 1 < nb) load_row32(first + 32 * (i + 1), rn);
+              if (ok && i + 1 < nb) {
+                if (first) load_row32(first + 32 * (i + 1), rn);
+                else if (rop) load_rop(rop + 32 * (i + 1), rn);
+              }
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {               // two halves of 16 columns: keeps the live registers low
                 float v[16];
@@ -419,6 +449,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
                   } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaf(ab, v[j], rr[j]);
+                  }
+                } else if (rop) {                             // decode the operand copy: undo its leaky-relu
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    float x;
+                    if constexpr (opf_is16(OPF)) {
+                      const uint32_t w = __float_as_uint(rc[8 * hh + (j >> 1)]);
+                      x = op16_to_float<OPF>((j & 1) ? (w >> 16) : (w & 0xffffu));
+                    } else {
+                      x = rr[j];
+                    }
+                    x = x > 0.f ? x : x * inv_slope;
+                    v[j] = beta * fmaf(alpha, v[j], x);
                   }
                 } else if (ab != 1.f) {
 #pragma unroll
@@ -579,9 +622,9 @@ bool aligned32(const qvc_tensor& t, size_t esize) {
 
 // Frames-on-rows pair kernel.  Returns QVC_ERR_UNSUPPORTED (error string untouched) when the layer is not one of its
 // cases.  QVC_TC_ROWS (bit mask): 1 = the gate layers of the WN stacks (384 columns), 2 = their 192 / 384-column LINEAR
-// layers, 4 = every eligible layer; 0 = never.
+// layers, 8 = the 128 -> 128 LINEAR layers (MRF-2), 4 = every eligible layer; 0 = never.
 int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
-  const int mode = tc_env_int("QVC_TC_ROWS", 3);
+  const int mode = tc_env_int("QVC_TC_ROWS", 11);
   if (mode <= 0) return QVC_ERR_UNSUPPORTED;
   if (a.epilogue != QVC_EPI_LINEAR && a.epilogue != QVC_EPI_GATE) return QVC_ERR_UNSUPPORTED;
   const bool gate = a.epilogue == QVC_EPI_GATE;
@@ -605,7 +648,8 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
   if (np == 0) return QVC_ERR_UNSUPPORTED;
   if (!(mode & 4)) {
     const bool wn_family = np == 192 && (a.cout == 192 || a.cout == 384);
-    if (!wn_family || !(mode & (gate ? 1 : 2))) return QVC_ERR_UNSUPPORTED;
+    const bool mrf2_family = !gate && a.cin == 128 && a.cout == 128;
+    if (!((wn_family && (mode & (gate ? 1 : 2))) || (mrf2_family && (mode & 8)))) return QVC_ERR_UNSUPPORTED;
   }
   const int npieces = a.cout / np;
   if (npieces > MAXPIECES) return QVC_ERR_UNSUPPORTED;
@@ -616,7 +660,7 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
   if (!aligned32(a.noise, 4)) return QVC_ERR_UNSUPPORTED;
   for (int s = 0; s < (gate ? 1 : a.nseg); ++s) {
     const qvc_epi_segment& g = a.seg[s];
-    if (g.res_op.ptr) return QVC_ERR_UNSUPPORTED;
+    if (!aligned32(g.res_op, esize)) return QVC_ERR_UNSUPPORTED;
     if (!aligned32(g.res, 4) || !aligned32(g.accin, 4) || !aligned32(g.raw, 4) || !aligned32(g.op, esize)) return QVC_ERR_UNSUPPORTED;
     if (!gate && (g.col0 % 32 || g.ncols % 32)) return QVC_ERR_UNSUPPORTED;
   }
@@ -647,9 +691,19 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
   p.bias_words = (!gate && a.bias && a.bias_bstride == 0 && a.cout <= 2048) ? a.cout : 0;
   p.slab_box_rows = (TM + halo + 7) & ~7;
   p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
-  p.w_stage_bytes = (uint32_t)(np / 2) * ROW_BYTES;
-  if (p.w_stage_bytes % 1024) return QVC_ERR_UNSUPPORTED;          // swizzle atoms: stages must stay 1024-byte aligned
-  static const int stage_options[][2] = {{4, 8}, {3, 8}, {3, 6}, {2, 6}, {2, 4}, {2, 3}, {2, 2}};
+  const uint32_t w_tap_bytes = (uint32_t)(np / 2) * ROW_BYTES;
+  if (w_tap_bytes % 1024) return QVC_ERR_UNSUPPORTED;              // swizzle atoms: every tap's tile must stay 1024-byte aligned
+  // taps per filter stage: as many as keep a stage at or under 32 KB, spread evenly over the groups
+  {
+    int tg = (int)(32768u / w_tap_bytes);
+    tg = tg < 1 ? 1 : (tg > a.k ? a.k : tg);
+    const int tg_env = tc_env_int("QVC_TCR_TG", 0);
+    if (tg_env >= 1 && tg_env <= a.k) tg = tg_env;
+    const int groups = (a.k + tg - 1) / tg;
+    p.tg = (a.k + groups - 1) / groups;
+  }
+  p.w_stage_bytes = (uint32_t)p.tg * w_tap_bytes;
+  static const int stage_options[][2] = {{4, 4}, {4, 3}, {3, 3}, {3, 2}, {2, 2}};
   size_t smem = 0;
   bool fits = false;
   {
@@ -681,11 +735,11 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05, rows): cuTensorMapEncodeTiled(x) failed: %d", (int)r); return QVC_ERR_CUDA; }
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)a.k * a.cin, (cuuint64_t)a.cout};
-    cuuint64_t strides[1] = {(cuuint64_t)a.k * a.cin * esize};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(np / 2)};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&p.mw, dt, 2, const_cast<void*>(a.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)a.k};
+    cuuint64_t strides[2] = {(cuuint64_t)a.k * a.cin * esize, (cuuint64_t)a.cin * esize};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)(np / 2), (cuuint32_t)p.tg};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&p.mw, dt, 3, const_cast<void*>(a.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv1d(tcgen05, rows): cuTensorMapEncodeTiled(w) failed: %d", (int)r); return QVC_ERR_CUDA; }
   }
@@ -702,11 +756,14 @@ int launch_conv_tcr(const qvc_conv_args& a, cudaStream_t stream) {
         if (c0 >= c1) continue;
         const int si = (a.nseg > 1 && c0 >= a.seg[1].col0) ? 1 : 0;
         const qvc_epi_segment& g = a.seg[si];
-        if (c0 < g.col0 || c1 > g.col0 + g.ncols || (g.res.ptr && g.accin.ptr)) lean = false;
+        if (c0 < g.col0 || c1 > g.col0 + g.ncols || ((g.res.ptr || g.res_op.ptr) && g.accin.ptr)) lean = false;
         if (si == 0 && a.nseg > 1 && c1 > a.seg[1].col0) lean = false;
       }
   }
   if (tc_env_int("QVC_TCR_LEAN", 1) == 0) lean = false;
+  if (!lean)                                        // the generic instance has no operand-format residual
+    for (int s = 0; s < (gate ? 0 : a.nseg); ++s)
+      if (a.seg[s].res_op.ptr) return QVC_ERR_UNSUPPORTED;
 #define QVC_TCR_DISPATCH(OPF)                                                                  \
   return gate ? launch_r<OPF, QVC_EPI_GATE, false>(p, 2 * pairs, smem, stream)                 \
               : (lean ? launch_r<OPF, QVC_EPI_LINEAR, true>(p, 2 * pairs, smem, stream)        \

@@ -390,7 +390,7 @@ extern "C" int qvc_wn_layer(const qvc_conv_args* gi, const qvc_conv_args* rs, qv
   cudaStream_t stream = (cudaStream_t)stream_;
   // Default: off whenever the frames-on-rows pair kernel is enabled (conv_tcr.cu, QVC_TC_ROWS): the layer then runs as its
   // two convolutions there, which is faster at every batch size measured (profiles/r02_summary.md).
-  if (!tc_env_int("QVC_WN_FUSED", (tc_env_int("QVC_TC_ROWS", 3) & 1) ? 0 : 1)) return QVC_ERR_UNSUPPORTED;
+  if (!tc_env_int("QVC_WN_FUSED", (tc_env_int("QVC_TC_ROWS", 11) & 1) ? 0 : 1)) return QVC_ERR_UNSUPPORTED;
   if (gi->backend != QVC_BACKEND_TCGEN05 || rs->backend != QVC_BACKEND_TCGEN05) return QVC_ERR_UNSUPPORTED;
   if (gi->opformat != rs->opformat || gi->opformat == QVC_OPF_F32) return QVC_ERR_UNSUPPORTED;
   if (gi->epilogue != QVC_EPI_GATE || rs->epilogue != QVC_EPI_LINEAR) return QVC_ERR_UNSUPPORTED;

@@ -195,6 +195,11 @@ bool use_frame_pairs(const Ctx& c, int li, int rows) {
   return enabled && c.m->backend == QVC_BACKEND_TCGEN05 && c.m->paired[li].w != nullptr && rows % 2 == 0;
 }
 
+bool rows_kernel_serves_mrf2() {
+  const char* e = getenv("QVC_TC_ROWS");               // read per call: tests switch it (default mask 11, conv_tcr.cu)
+  return ((e ? atoi(e) : 11) & (8 | 4)) != 0;
+}
+
 // arguments of layer li in frame-paired form: x holds `rows` frames of `ch` channels with row pitch ch
 qvc_conv_args paired_args(const Ctx& c, int li, const void* x, int64_t bs, int batch, int rows, int ch) {
   const qvc_layer& L = c.m->paired[li];
@@ -325,7 +330,14 @@ int run_mrf(const Ctx& c, int cb, int rows, int ch, int l_res0, float* x1R, void
     const void* srcO = x1O;
     for (int j = 0; j < 3; ++j) {
       // frame-paired layers see every tensor as [rows / 2][2 ch]: the same memory with the row pitch doubled
-      const bool p1 = use_frame_pairs(c, lb + j, rows), p2 = use_frame_pairs(c, lb + 3 + j, rows);
+      // 128-channel layers run in their PLAIN form wherever the frames-on-rows pair kernel serves the family (conv_tcr.cu,
+      // QVC_TC_ROWS bit 8: measured faster than the frame-paired channel-major form on every MRF-2 layer,
+      // profiles/r02_summary.md) -- at every batch size, so that an utterance's samples do not depend on what it is
+      // batched with: small shapes then run the same form on conv_tc, whose accumulation order is the same.  The blocks'
+      // last convolutions (j == 2) keep the form the sum kernel shares.
+      const bool plain_mrf2 = c.m->backend == QVC_BACKEND_TCGEN05 && rows_kernel_serves_mrf2();
+      const bool p1 = !plain_mrf2 && use_frame_pairs(c, lb + j, rows);
+      const bool p2 = !(plain_mrf2 && (j < 2 || !fused_sum)) && use_frame_pairs(c, lb + 3 + j, rows);
       const int w1 = p1 ? 2 * ch : ch, w2 = p2 ? 2 * ch : ch;
       qvc_conv_args a = p1 ? paired_args(c, lb + j, srcO, bs, cb, rows, ch)
                            : layer_args(c, lb + j, tens(srcO, bs, ch), cb, rows, rows);

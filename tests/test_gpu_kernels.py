@@ -264,6 +264,35 @@ def test_rows_kernel_linear(geom, opf, monkeypatch):
     assert float((op.cpu().double() - want_op).abs().max()) < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11)) * scale
 
 
+@pytest.mark.parametrize("opf", TC_OPFS, ids=TC_IDS)
+@pytest.mark.parametrize("geom", [(2, 300, 128, 128, 3), (3, 700, 128, 128, 7), (1, 515, 256, 256, 11)],
+                         ids=["128ch-k3", "128ch-k7", "256ch-k11"])
+def test_rows_kernel_residual_from_operand_copy(opf, geom, monkeypatch):
+    """seg.res_op on the frames-on-rows kernel (the c2 layers of MRF-2 in the 16-bit modes): the residual arrives as the
+    operand-format copy of leaky_relu(r, 0.1); tap-grouped filter stages (3, 4 + 3 and 2 x 6 taps per TMA operation)."""
+    _force_rows(monkeypatch)
+    B, rows, cin, cout, k = geom
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = to_op(torch.randn(B, rows, cin, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(cout, k, cin, generator=g) / (cin * k) ** 0.5, opf).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    r = torch.randn(B, rows, cout, generator=g)
+    r_op = to_op(torch.where(r > 0, r, 0.1 * r), opf).to(DEV)
+    raw = torch.full((B, rows, cout), float("nan"), device=DEV)
+    op = torch.zeros(B, rows, cout, device=DEV, dtype=op_dtype(opf))
+    conv1d(x, w, bias, k=k, dil=1, pad_left=(k - 1) // 2, out_rows=rows, opf=opf, backend=capi.BACKEND_TCGEN05,
+           segs=[dict(col0=0, ncols=cout, slope=0.1, res_op=r_op, res_inv_slope=10.0, raw=raw, op=op)])
+    assert capi.last_kernel() == "conv_tcr_kernel"
+    torch.cuda.synchronize()
+    acc = ref_conv(x.cpu().float(), w.cpu().float(), k, 1, (k - 1) // 2, rows)
+    rq = r_op.cpu().double()
+    want = acc + bias.cpu().double() + torch.where(rq > 0, rq, rq * 10.0)
+    scale = float(want.abs().max())
+    assert float((raw.cpu().double() - want).abs().max()) < _tol(opf) * scale
+    want_op = torch.where(want > 0, want, want * 0.1)
+    assert float((op.cpu().double() - want_op).abs().max()) < (_tol(opf) + (2 ** -8 if opf == capi.OPF_BF16 else 2 ** -11)) * scale
+
+
 @pytest.mark.parametrize("be", BACKENDS, ids=IDS)
 @pytest.mark.parametrize("per_utt_bias", [False, True])
 @pytest.mark.parametrize("rows", [45, 300], ids=["R45", "R300"])      # R300: the CTA-pair (cta_group::2) gate kernel
