@@ -228,6 +228,15 @@ typedef struct {
 int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, int batch, int frames,
              const int32_t* live_units, int frames_per_unit, float* wave, float* y_mb, qvc_stream_t stream);
 
+/* subband_conv_post AND the tail in one launch (tcgen05 back end): `post` describes the post-net convolution as for
+ * qvc_conv1d (x = the reflection-padded 128-channel operand series, cout = 80 with 72 live rows, k = 7, QVC_EPI_LINEAR;
+ * seg[0].raw, optional, receives a copy of the 72-channel post-net output), and the kernel's epilogue is qvc_tail: the
+ * 72-channel tensor is never written and read back.  wave / y_mb / live_units as for qvc_tail with frames = post->out_rows.
+ * Returns QVC_ERR_UNSUPPORTED (error string untouched) when the fused kernel does not apply (FMA back end, tail weights
+ * without host copies, other shapes): the caller then issues qvc_conv1d + qvc_tail. */
+int qvc_post_tail(const qvc_conv_args* post, const qvc_tail_weights* w, const int32_t* live_units, int frames_per_unit,
+                  float* wave, float* y_mb, qvc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Whole path
  * ------------------------------------------------------------------------------------------- */

@@ -103,6 +103,8 @@ SYMBOLS = {
                                   C.c_size_t, C.c_void_p]),
     "qvc_tail": (C.c_int, [C.POINTER(TailWeights), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qvc_post_tail": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(TailWeights), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
     "qvc_infer_workspace_bytes": (C.c_size_t, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int]),
     "qvc_infer": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -528,7 +528,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
         mbar_wait(tmem_full + 8 * buf, bph);
         tc_fence_after();
         const int nun = hp >> 4;                    // units of 16 gate channels; this group takes half of them
-        const int u0 = h ? (nun + 1) >> 1 : 0, u1 = h ? nun : (nun + 1) >> 1;
+        const int u0 = h ? (nun + 1) >> 1 : 0, u1 = (p.debug & 1) ? 0 : (h ? nun : (nun + 1) >> 1);
         for (int u = u0; u < u1; ++u) {
           float lo[16], hi[16];
           tmem_ld16(taddr + 16 * u, lo);

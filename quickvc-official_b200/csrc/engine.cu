@@ -464,15 +464,25 @@ int run_decoder(const Ctx& whole, const Buffers& bf, const Shapes& s, const void
     {
       qvc_conv_args a = layer_args(c, L_POST, tens(bf.pO, (int64_t)RP * C_UP1, C_UP1), cb, RP, RP);
       a.seg[0] = seg(0, C_POST);
-      a.seg[0].raw = tens(bf.cpR, (int64_t)RP * C_POST, C_POST);
-      QVC_PROPAGATE(run(c, a));
-      if (taps && taps->conv_post)
+      float* y_mb = (taps && taps->y_mb) ? taps->y_mb + (size_t)b0 * 4 * 4 * R1 : nullptr;
+      // post-net convolution and tail in one launch (post_tail.cu): the 72-channel tensor only exists when a tap asks for it
+      const bool tap = taps && taps->conv_post;
+      if (tap) a.seg[0].raw = tens(bf.cpR, (int64_t)RP * C_POST, C_POST);
+      int st = QVC_ERR_UNSUPPORTED;
+      if (c.m->backend == QVC_BACKEND_TCGEN05)
+        st = qvc_post_tail(&a, &c.m->tail, c.lengths, UP0 * UP1, wave + (size_t)b0 * 16 * R1, y_mb, (qvc_stream_t)c.st);
+      if (st == QVC_ERR_UNSUPPORTED) {
+        a.seg[0].raw = tens(bf.cpR, (int64_t)RP * C_POST, C_POST);
+        QVC_PROPAGATE(run(c, a));
+        QVC_PROPAGATE(qvc_tail(&c.m->tail, bf.cpR, C_POST, cb, RP, c.lengths, UP0 * UP1, wave + (size_t)b0 * 16 * R1, y_mb,
+                               (qvc_stream_t)c.st));
+      } else {
+        QVC_PROPAGATE(st);
+      }
+      if (tap)
         QVC_PROPAGATE(from_series_major(bf.cpR, C_POST, (int64_t)RP * C_POST, taps->conv_post + (size_t)b0 * C_POST * RP,
                                         cb, C_POST, RP, false, c.st));
     }
-    QVC_PROPAGATE(qvc_tail(&c.m->tail, bf.cpR, C_POST, cb, RP, c.lengths, UP0 * UP1, wave + (size_t)b0 * 16 * R1,
-                           (taps && taps->y_mb) ? taps->y_mb + (size_t)b0 * 4 * 4 * R1 : nullptr,
-                           (qvc_stream_t)c.st));
   }
   return QVC_OK;
 }

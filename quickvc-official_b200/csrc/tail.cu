@@ -11,7 +11,6 @@
 //
 // Algorithmic bytes per post-net frame: 72*4 read + 16*4 written = 352 B.
 #include <cstring>
-#include <mutex>
 
 #include "common.cuh"
 
@@ -192,9 +191,7 @@ extern "C" int qvc_tail(const qvc_tail_weights* w, const float* post, int ld, in
   const int ny = 4 * (frames - 1);
   if (batch == 0 || ny == 0) return QVC_OK;
   QVC_REQUIRE(batch <= 65535, "qvc_tail: batch too large for one launch");
-  static TailParams p;                    // ~1.2 KB: not on the stack twice; filled and launched under the lock
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lk(mu);
+  TailParams p;                           // ~1.2 KB on the stack: launches from several host threads do not serialise
   p.post = post; p.ld = ld; p.frames = frames; p.window = w->window; p.synth = w->synth; p.wave = wave; p.y_mb = y_mb;
   p.live_units = live_units; p.frames_per_unit = frames_per_unit;
   dim3 grid((ny + TQ - 1) / TQ, batch);

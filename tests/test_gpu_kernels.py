@@ -389,6 +389,67 @@ def test_tail_matches_oracle(frames, batch, sd):
     assert torch.equal(wave2, wave)
 
 
+@pytest.mark.parametrize("opf", TC_OPFS, ids=TC_IDS)
+@pytest.mark.parametrize("frames,batch,ragged", [(2, 1, False), (17, 3, False), (122, 2, False), (123, 1, False), (481, 2, True),
+                                                 (1001, 3, True), (10001, 2, False)])
+def test_fused_post_net_and_tail_equals_the_two_launches(opf, frames, batch, ragged, sd):
+    """qvc_post_tail (subband_conv_post as a tcgen05 GEMM whose epilogue is the tail) against qvc_conv1d + qvc_tail on the
+    same operands: tile edges (121 frames per CTA, 242 per pair), the overlap-add / FIR halo recomputed per tile, ragged
+    lengths, and the optional post-net and sub-band taps."""
+    lib = capi.load()
+    be = capi.BACKEND_TCGEN05
+    g = torch.Generator(device="cpu").manual_seed(frames)
+    x = to_op(0.5 * torch.randn(batch, frames, 128, generator=g), opf).to(DEV)
+    w = to_op(torch.randn(80, 7, 128, generator=g) / (128 * 7) ** 0.5, opf)
+    w[72:] = 0
+    w = w.to(DEV)
+    bias = (0.3 * torch.randn(80, generator=g))
+    bias[72:] = 0
+    bias = bias.to(DEV)
+    f = fold.fold_state_dict({k: v for k, v in sd.items() if not k.startswith("enc_q.")}, capi.OPF_F32)
+    win, syn = f.tensors["tail.window"].to(DEV), f.tensors["tail.synth"].to(DEV)
+    tw = capi.TailWeights(win.data_ptr(), syn.data_ptr(), f.tensors["tail.window_host"].data_ptr(),
+                          f.tensors["tail.synth_host"].data_ptr())
+    fpu = 20
+    lens = None
+    if ragged:                                     # frames = 20 * units + 1
+        units = (frames - 1) // fpu
+        lens = torch.tensor([max(1, units - 7 * i) for i in range(batch)], dtype=torch.int32, device=DEV)
+    lp = lens.data_ptr() if lens is not None else None
+    # two launches: the convolution writes the 72-channel tensor, the tail reads it back
+    post = torch.zeros(batch, frames, 72, device=DEV)
+    a = make_args(x, w, bias, k=7, dil=1, pad_left=3, out_rows=frames, opf=opf, backend=be, segs=[dict(col0=0, ncols=72, raw=post)])
+    capi.check(lib.qvc_conv1d(C.byref(a), stream()), "qvc_conv1d")
+    wave0 = torch.full((batch, 1, 16 * (frames - 1)), float("nan"), device=DEV)
+    ymb0 = torch.full((batch, 4, 4 * (frames - 1)), float("nan"), device=DEV)
+    capi.check(lib.qvc_tail(C.byref(tw), post.data_ptr(), 72, batch, frames, lp, fpu, wave0.data_ptr(), ymb0.data_ptr(), stream()), "qvc_tail")
+    # one launch, with both taps
+    post1 = torch.full((batch, frames, 72), float("nan"), device=DEV)
+    a1 = make_args(x, w, bias, k=7, dil=1, pad_left=3, out_rows=frames, opf=opf, backend=be, segs=[dict(col0=0, ncols=72, raw=post1)])
+    wave1 = torch.full_like(wave0, float("nan"))
+    ymb1 = torch.full_like(ymb0, float("nan"))
+    capi.check(lib.qvc_post_tail(C.byref(a1), C.byref(tw), lp, fpu, wave1.data_ptr(), ymb1.data_ptr(), stream()), "qvc_post_tail")
+    assert capi.last_kernel() == "post_tail_kernel"
+    # ... and without them
+    a2 = make_args(x, w, bias, k=7, dil=1, pad_left=3, out_rows=frames, opf=opf, backend=be, segs=[dict(col0=0, ncols=72)])
+    wave2 = torch.full_like(wave0, float("nan"))
+    capi.check(lib.qvc_post_tail(C.byref(a2), C.byref(tw), lp, fpu, wave2.data_ptr(), None, stream()), "qvc_post_tail")
+    torch.cuda.synchronize()
+    tol = 2e-5 if opf != capi.OPF_BF16 else 2e-3         # accumulation order of the GEMM only: operands are pre-rounded
+    scale = float(wave0.abs().max()) + 1e-9
+    assert not torch.isnan(wave1).any() and not torch.isnan(ymb1).any()
+    assert float((wave1 - wave0).abs().max()) < tol * scale
+    assert float((ymb1 - ymb0).abs().max()) < tol * (float(ymb0.abs().max()) + 1e-9)
+    assert torch.equal(wave2, wave1)
+    if lens is None:
+        assert float((post1 - post).abs().max()) < tol * float(post.abs().max())
+    else:
+        for b in range(batch):
+            n = int(lens[b]) * fpu + 1
+            assert float((post1[b, :n] - post[b, :n]).abs().max()) < tol * float(post.abs().max())
+            assert float(wave1[b, 0, 16 * (n - 1):].abs().max() if n < frames else 0.0) == 0.0
+
+
 @pytest.mark.parametrize("bm,tm", [(1, 129), (1, 250), (1, 500), (1, 1500), (3, 100), (1, 128), (9, 7)])
 @pytest.mark.parametrize("spc", [None, 1, 4, 8])
 def test_speaker_encoder_matches_oracle(bm, tm, spc, sd, monkeypatch):
