@@ -29,7 +29,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FLOP_PER_FRAME = 207.2e6          # conv/linear FLOPs per unit frame per utterance
 FLOP_PER_WINDOW = 356.5e6         # speaker-encoder LSTM FLOPs per 128-frame mel window
-TAIL_BYTES_PER_POST_FRAME = 72 * 4 + 16 * 4   # read 72 fp32 channels, write 16 fp32 samples
+TAIL_BYTES_PER_POST_FRAME = 128 * 4 + 16 * 4  # fused definition: 128-channel MRF output in (fp32), 16 fp32 samples out = 576,000 B per audio-second
 DECODER_FLOP_PER_UTT_10S = 89.36e9            # decoder-only conv FLOPs per 10 s utterance
 
 
@@ -459,9 +459,10 @@ def run_ours(args, rank, local_rank, world):
     if tf32 and os.path.exists(tf32_path):
         with open(tf32_path) as f:
             cublas_tf32 = json.load(f)["tf32_tflops_sustained"]
-    traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.precision == "tf32" and B == 64 and T == 500:
+    traffic, traffic_note, tj = None, None, None
+    tpath = next((q for q in (os.path.join(ROOT, "profiles", f"r02_traffic_{args.precision}.json"),
+                              os.path.join(ROOT, "profiles", "r01_traffic.json")) if os.path.exists(q)), None)
+    if tpath and (args.precision == "tf32" or "r02" in tpath) and B == 64 and T == 500:
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["conv_tc"]["dram_bytes_per_launch"]
@@ -469,7 +470,9 @@ def run_ours(args, rank, local_rank, world):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_note": traffic_note,
-        "kernel": "conv_tc_kernel + conv_tc2_kernel + conv_wn_kernel (tcgen05 implicit-GEMM series convolution: cta_group::1, CTA-pair cta_group::2, and the fused WN-layer variant)",
+        "kernel": "conv_tcr_kernel + conv_tc2_kernel + conv_tc_kernel + post_tail_kernel (tcgen05 implicit-GEMM series convolution: "
+                  "CTA pairs with frames on the accumulator rows, CTA pairs with channels on them, cta_group::1, and the post-net "
+                  "convolution whose epilogue is the iSTFT / overlap-add / synthesis tail)",
         "launches_per_step": int(conv_launches), "avg_launch_us": conv_ms_step * 1e3 / max(1, conv_launches),
         "kernel_ms_per_step": conv_ms_step, "kernel_share_of_step": conv_ms_step / ms,
         "flops_per_step": conv_flops,
@@ -508,20 +511,38 @@ def run_ours(args, rank, local_rank, world):
         line["sweep_4096_bf16"] = sweep
 
     if not args.no_extras and world == 1:
-        # tail kernel alone: HBM roofline of the fused iSTFT / OLA / synthesis kernel
+        # the fused post-net convolution + iSTFT / overlap-add / synthesis kernel (post_tail.cu) alone, on the HBM roofline of
+        # SURVEY.md section 8d's fused definition: the 128-channel operand series in, the waveform out
         frames_post = 20 * T + 1
-        post = torch.randn(B, frames_post, 72, device=dev) * 0.3
-        wave = torch.empty(B, 1, 320 * T, device=dev)
         model = net._engine._ensure_model(dev)
         stream = torch.cuda.current_stream().cuda_stream
-        ms_tail, _ = timed(lambda: capi.check(lib.qvc_tail(C.byref(model.tail), post.data_ptr(), 72, B, frames_post,
-                                                           None, 0, wave.data_ptr(), None, stream), "qvc_tail"), 20, 3)
+        esz = 4 if args.precision in ("tf32", "fp32") else 2
+        odt = {"tf32": torch.float32, "fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[args.precision]
+        xin = (torch.randn(B, frames_post, 128, device=dev) * 0.3).to(odt)
+        wave = torch.empty(B, 1, 320 * T, device=dev)
+        L = model.layers[capi.QVC_NUM_LAYERS - 1]
+        pa = capi.ConvArgs()
+        pa.x = capi.Tensor(xin.data_ptr(), frames_post * 128, 128, 0)
+        pa.batch, pa.x_rows, pa.out_rows, pa.cin = B, frames_post, frames_post, 128
+        pa.w, pa.bias, pa.bias_bstride = L.w, L.bias, 0
+        pa.cout, pa.k, pa.dil, pa.pad_left = L.cout, L.k, L.dil, L.pad_left
+        pa.epilogue, pa.nseg = 0, 1
+        pa.seg[0].col0, pa.seg[0].ncols, pa.seg[0].alpha, pa.seg[0].beta, pa.seg[0].slope = 0, 72, 1.0, 1.0, 1.0
+        pa.opformat, pa.backend = model.opformat, model.backend
         tail_bytes = B * frames_post * TAIL_BYTES_PER_POST_FRAME
-        line["tail_roofline"] = {"bound": "hbm", "achieved": tail_bytes / (ms_tail * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                 "frac": tail_bytes / (ms_tail * 1e-3) / 1e9 / pk["hbm"],
-                                 "traffic": (tj["tail"]["dram_bytes_per_launch"] if traffic is not None else None), "ms": ms_tail,
-                                 "algorithmic_bytes": tail_bytes,
-                                 "peak_source": pk["source"]}
+        if lib.qvc_post_tail(C.byref(pa), C.byref(model.tail), None, 0, wave.data_ptr(), None, stream) == 0:
+            ms_tail, _ = timed(lambda: capi.check(lib.qvc_post_tail(C.byref(pa), C.byref(model.tail), None, 0, wave.data_ptr(),
+                                                                    None, stream), "qvc_post_tail"), 20, 3)
+            line["tail_roofline"] = {
+                "bound": "hbm", "achieved": tail_bytes / (ms_tail * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": tail_bytes / (ms_tail * 1e-3) / 1e9 / pk["hbm"],
+                "traffic": (tj["tail"]["dram_bytes_per_launch"] if tj is not None and "tail" in tj else None), "ms": ms_tail,
+                "algorithmic_bytes": tail_bytes, "actual_bytes": B * frames_post * (128 * esz + 64),
+                "kernel": "post_tail_kernel: subband_conv_post (tcgen05, frames on the accumulator rows) with the magnitude exp / "
+                          "phase sin-cos, 16-point inverse DFT, windowed overlap-add and synthesis FIR as its epilogue",
+                "note": "measured issue-bound (polar + DFT + 272 FMAs of synthesis FIR per sub-band sample on 8 epilogue warps), "
+                        "not HBM-bound: profiles/r02_summary.md",
+                "peak_source": pk["source"]}
         # the separately reported bf16 mode, and the p50 latency of one 5 s clip
         if args.precision == "tf32":
             nb = make_net("bf16")
@@ -617,7 +638,7 @@ def run_ours(args, rank, local_rank, world):
                                 "live_audio_s": live_s, "padded_audio_s": B * T / 50.0,
                                 "note": f"infer(unit, mel, lengths=...) on {B} utterances of 5..10 s padded to 10 s: each gets "
                                         "exactly the samples of its own single-utterance call (tests/test_gpu_ragged.py); "
-                                        "padding frames are computed and masked, so the step time equals the dense batch's"}
+                                        "tiles wholly past an utterance's end are skipped by every warp role"}
 
         # SURVEY.md section 8f "next" #1: the target-mel front end (wave_to_mel, convert.py:75-77) for one 10 s target
         from quickvc_official_b200 import mel as qmel

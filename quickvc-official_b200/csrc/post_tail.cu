@@ -96,7 +96,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) post_ta
   // epilogue work area: bias, squared window, windowed frame samples, trimmed sub-band signal
   float* bias_s = reinterpret_cast<float*>(tmem_slot_ptr + 4);
   float* W2 = bias_s + NCOL;
-  float (*Xf)[TMR][17] = reinterpret_cast<float (*)[TMR][17]>(W2 + 16);
+  float* inv_env = W2 + 16;                 // 1 / (sum of the four squared window values that overlap at position n mod 4)
+  float (*Xf)[TMR][17] = reinterpret_cast<float (*)[TMR][17]>(inv_env + 4);
   float (*Y)[YW] = reinterpret_cast<float (*)[YW]>(&Xf[4][0][0]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,6 +117,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) post_ta
   }
   for (int i = threadIdx.x; i < NCOL; i += blockDim.x) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   if (threadIdx.x < 16) W2[threadIdx.x] = p.Wc[threadIdx.x] * p.Wc[threadIdx.x];
+  if (threadIdx.x < 4) {
+    const int i = threadIdx.x;
+    inv_env[i] = 1.f / (((p.Wc[i] * p.Wc[i] + p.Wc[i + 4] * p.Wc[i + 4]) + p.Wc[i + 8] * p.Wc[i + 8]) + p.Wc[i + 12] * p.Wc[i + 12]);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -252,22 +257,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) post_ta
             re[kk] = mag * cs;
             im[kk] = mag * sn;
           }
-          // x[n] = A[n] - Bo[n], x[16-n] = A[n] + Bo[n]; Im of DC / Nyquist is ignored (irfft)
+          // x[n] = A[n] - Bo[n], x[16-n] = A[n] + Bo[n]; Im of DC / Nyquist is ignored (irfft).  Even / odd bins:
+          //   A[n] = Ae[n] + Ao[n], A[8-n] = Ae[n] - Ao[n];   Bo[n] = Be[n] + Bd[n], Bo[8-n] = Bd[n] - Be[n]
+          // (cos(2 pi k (8-n) / 16) = (-1)^k cos(2 pi k n / 16), sin likewise with the opposite sign): n = 0..4 only.
+          float xs[17];
 #pragma unroll
-          for (int n = 0; n <= 8; ++n) {
-            float a = re[0] + ((n & 1) ? -re[8] : re[8]);
-            float bo = 0.f;
+          for (int n = 0; n <= 4; ++n) {
+            float ae = re[0] + re[8], ao = 0.f, be = 0.f, bd = 0.f;
 #pragma unroll
             for (int kk = 1; kk < 8; ++kk) {
               const int m = (kk * n) & 15;
-              a = fmaf(2.f * re[kk], pt_cos16[m], a);
-              bo = fmaf(2.f * im[kk], pt_cos16[(m + 12) & 15], bo);
+              if (kk & 1) {
+                ao = fmaf(2.f * re[kk], pt_cos16[m], ao);
+                bd = fmaf(2.f * im[kk], pt_cos16[(m + 12) & 15], bd);
+              } else {
+                ae = fmaf(2.f * re[kk], pt_cos16[m], ae);
+                be = fmaf(2.f * im[kk], pt_cos16[(m + 12) & 15], be);
+              }
             }
-            a *= 0.0625f;
-            bo *= 0.0625f;
-            Xf[s][row][n] = (a - bo) * p.Wc[n];
-            if (n >= 1 && n <= 7) Xf[s][row][16 - n] = (a + bo) * p.Wc[16 - n];
+            if (n & 1) ae -= 2.f * re[8];            // the Nyquist bin enters as (-1)^n re[8]
+            const float a1 = 0.0625f * (ae + ao), b1 = 0.0625f * (be + bd);       // A[n], Bo[n]
+            const float a2 = 0.0625f * (ae - ao), b2 = 0.0625f * (bd - be);       // A[8-n], Bo[8-n]
+            xs[n] = a1 - b1;
+            xs[16 - n] = a1 + b1;
+            xs[8 - n] = a2 - b2;
+            xs[8 + n] = a2 + b2;
           }
+#pragma unroll
+          for (int n = 0; n < 16; ++n) Xf[s][row][n] = xs[n] * p.Wc[n];
         }
       };
       if (frame_ok) {
@@ -276,27 +293,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) post_ta
       }
       epi_bar_sync();
 
-      // 2. overlap-add, envelope, trim: Y[s][i] = y[s][q0 - 8 + i]
-      for (int i = te; i < 4 * YW; i += N_EPI_THREADS) {
-        const int s = i / YW, ii = i % YW;
-        const int qq = q0 - 8 + ii;
-        float v = 0.f;
-        if (qq >= 0 && qq < ny) {
-          const int pos = qq + 8;
-          const int fhi = pos >> 2;
-          float a = 0.f, env = 0.f;
+      // 2. overlap-add, envelope, trim: Y[s][i] = y[s][q0 - 8 + i].  Away from the utterance's edges four frames overlap at
+      // every position and the envelope only depends on the position modulo the hop: a multiplication by one of four
+      // reciprocals; the first and last three frames take the general path.
+      for (int s = 0; s < 4; ++s) {
+        for (int ii = te; ii < YW; ii += N_EPI_THREADS) {
+          const int qq = q0 - 8 + ii;
+          float v = 0.f;
+          if (qq >= 0 && qq < ny) {
+            const int pos = qq + 8;
+            const int fhi = pos >> 2, n0 = pos & 3;
+            if (fhi >= 3 && fhi < F) {
+              const float* xr = &Xf[s][fhi - f_lo][n0];
+              const float a = (xr[0] + xr[4 - 17]) + (xr[8 - 34] + xr[12 - 51]);
+              v = a * inv_env[n0];
+            } else {
+              float a = 0.f, env = 0.f;
 #pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            const int ff = fhi - dd;
-            const int n = pos - 4 * ff;
-            if (ff >= 0 && ff < F) {
-              a += Xf[s][ff - f_lo][n];
-              env += W2[n];
+              for (int dd = 0; dd < 4; ++dd) {
+                const int ff = fhi - dd;
+                const int n = pos - 4 * ff;
+                if (ff >= 0 && ff < F) {
+                  a += Xf[s][ff - f_lo][n];
+                  env += W2[n];
+                }
+              }
+              v = a / env;
             }
           }
-          v = a / env;
+          Y[s][ii] = v;
         }
-        Y[s][ii] = v;
       }
       epi_bar_sync();
 
@@ -415,7 +441,7 @@ extern "C" int qvc_post_tail(const qvc_conv_args* post, const qvc_tail_weights* 
   p.slab_box_rows = (TMR + a.k - 1 + 7) & ~7;
   p.slab_stage_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
   p.slab_stages = 4; p.w_stages = 3;
-  const size_t epi_bytes = 4 * (size_t)(NCOL + 16 + 4 * TMR * 17 + 4 * YW);
+  const size_t epi_bytes = 4 * (size_t)(NCOL + 16 + 4 + 4 * TMR * 17 + 4 * YW);
   const size_t smem = (size_t)p.slab_stages * p.slab_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes + 1024 + 256 + epi_bytes;
   if (smem > (size_t)MAX_SMEM) return QVC_ERR_UNSUPPORTED;
 
