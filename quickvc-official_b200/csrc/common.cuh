@@ -89,9 +89,14 @@ template <> __device__ __forceinline__ __nv_bfloat16 to_operand<QVC_OPF_BF16>(fl
   return __float2bfloat16_rn(v);
 }
 
-// half saturates instead of overflowing to infinity: one out-of-range activation must not poison a whole utterance
-__device__ __forceinline__ float clamp_half_range(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
-template <> __device__ __forceinline__ __half to_operand<QVC_OPF_F16>(float v) { return __float2half_rn(clamp_half_range(v)); }
+// half saturates instead of overflowing to infinity: one out-of-range activation must not poison a whole utterance.
+// cvt.rn.satfinite is ONE instruction (F2FP.SATFINITE); the two-FMNMX clamp it replaces made every fp16 epilogue 2
+// instructions per element heavier than the bf16 one (a memory-bound MRF-2 layer: 95 us against 83, profiles/r02_summary.md).
+template <> __device__ __forceinline__ __half to_operand<QVC_OPF_F16>(float v) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return __ushort_as_half(h);
+}
 
 __device__ __forceinline__ float op_to_float(float v) { return v; }
 __device__ __forceinline__ float op_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -110,8 +115,9 @@ __device__ __forceinline__ uint32_t op16_pack2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
   } else {
-    __half2 t = __floats2half2_rn(clamp_half_range(lo), clamp_half_range(hi));
-    return *reinterpret_cast<uint32_t*>(&t);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
 }
 
