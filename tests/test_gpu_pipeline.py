@@ -60,3 +60,34 @@ def test_graphed_infer_replays_the_same_arithmetic():
     # without a supplied noise the draw happens inside the static buffer: finite output of the right shape
     out = graphed(unit, mel)
     assert out.shape == (B, 1, 320 * T) and bool(torch.isfinite(out).all())
+
+
+def test_host_gather_equals_infer(sd, model_cfg):
+    """shard.HostGather on one GPU: the shared, page-locked host buffer receives exactly net.infer's waveforms, chunk by
+    chunk on the side stream (the N-rank form is covered on gloo in tests/test_shard.py)."""
+    from quickvc_official_b200.shard import HostGather
+    net = SynthesizerTrn(641, 32, **model_cfg, precision="tf32").eval()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    n, t = 5, 40
+    unit, mel, noise = synth.synthetic_inputs(n, t, 1, 150, 3)
+    u, m = unit.to(DEV), mel.to(DEV)
+    torch.manual_seed(0)
+    want = net.infer(u, m, noise=noise.to(DEV))
+    hg = HostGather(n, 320 * t, name="qvc_test_gather_gpu")
+    try:
+        nz = noise.to(DEV)
+        pos = [0]
+
+        def infer(uu, mm):
+            k = uu.shape[0]
+            out = net.infer(uu, mm, noise=nz[pos[0]:pos[0] + k])
+            pos[0] += k
+            return out
+
+        got = hg.convert(infer, u, m, chunk=2)
+        hg.finish(DEV)
+        assert got.shape == (n, 1, 320 * t) and not got.is_cuda
+        assert torch.equal(got, want.cpu())
+    finally:
+        hg.close()

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from quickvc_official_b200.shard import convert_sharded, shard_range
+from quickvc_official_b200.shard import HostGather, convert_sharded, shard_range
 
 
 def test_shard_range_partitions_contiguously():
@@ -46,6 +46,17 @@ def _worker(rank, world, port, n, t, ret):
         mine = convert_sharded(_fake_infer, unit, mel, gather=False)
         lo, hi = shard_range(n, world, rank)
         assert torch.equal(mine, _fake_infer(unit[lo:hi], mel))
+        # the host gather: every rank copies its own rows into one shared host buffer, two utterances per call
+        hg = HostGather(n, 320 * t, name=f"qvc_test_gather_{port}_{n}")
+        try:
+            got = hg.convert(_fake_infer, unit, mel, chunk=2)
+            hg.finish()
+            if rank == 0:
+                ret["host_ok"] = bool(torch.equal(got, _fake_infer(unit, mel)))
+            else:
+                assert got is None
+        finally:
+            hg.close()
     finally:
         dist.destroy_process_group()
 
@@ -63,6 +74,7 @@ def test_convert_sharded_two_ranks_gloo(n):
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, _free_port(), n, t, ret), nprocs=world, join=True)
         assert ret["ok"] and ret["shape"] == (n, 1, 320 * t)
+        assert ret["host_ok"]
 
 
 def test_convert_sharded_single_process():
