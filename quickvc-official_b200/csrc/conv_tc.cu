@@ -119,34 +119,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   // of this grid got here (its barrier init / TMEM allocation / tensor-map prefetch then overlap our main
   // loop's tail); nothing above touched global memory, everything below waits for the previous grid.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // Filters are constants: the producer requests the first filter stages of this CTA's first tile BEFORE waiting for the
-  // previous grid, so their L2 / HBM latency runs under that grid's tail (a single clip is a chain of ~125 such kernels
-  // whose every first load would otherwise start after the wait).  Dense batches only: the ragged tile list needs `live`.
-  uint32_t pre_w = 0;                               // filter stages requested ahead (producer thread only)
-  if (warp == 0 && lane == 0) {
-    for (int si = 0; si < nsrc; ++si) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.src[si].mx) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.src[si].mw) : "memory");
-    }
-    if (p.ep.live == nullptr && !(p.debug & 1) && (int)blockIdx.x < p.ntiles) {
-      const int gi = (int)blockIdx.x % p.ngroups, gs = p.gsize[gi];
-      const Src1& S = p.src[0];
-      uint32_t tp = 0;
-      if constexpr (TAPS) tp = S.taps[gs > 1 ? 2 : (p.row0[gi][0] >= p.cout_half ? 1 : 0)];
-      for (int cc = 0; cc < S.cin / KC && pre_w < (uint32_t)p.w_stages; ++cc) {
-        int jbeg = 0, jend = S.k - 1;
-        if constexpr (TAPS) {
-          const uint32_t r = cc >= S.split_chunk ? tp >> 8 : tp;
-          jbeg = (int)(r & 15u); jend = (int)((r >> 4) & 15u);
-        }
-        for (int j = jbeg; j <= jend && pre_w < (uint32_t)p.w_stages; ++j, ++pre_w) {
-          mbar_expect_tx(full_w + 8 * pre_w, (uint32_t)gs * CHUNK_BYTES);
-          for (int ci = 0; ci < gs; ++ci)
-            tma_load_2d(w0 + pre_w * p.w_stage_bytes + ci * CHUNK_BYTES, &S.mw, full_w + 8 * pre_w, j * S.cin + cc * KC, p.row0[gi][ci]);
-        }
-      }
-    }
-  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.ep.live != nullptr) {
     load_live_cache(p.ep, p.batch, live_s);
@@ -156,6 +128,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      for (int si = 0; si < nsrc; ++si) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.src[si].mx) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.src[si].mw) : "memory");
+      }
       // stage indices / phase parities are carried incrementally: a runtime integer division per K block
       // on this single thread (I2F / MUFU.RCP chains) cost more than the MMAs it feeds
       uint32_t s = 0, ph = 0, ws = 0, wph = 0;
@@ -186,16 +162,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               jbeg = (int)(r & 15u); jend = (int)((r >> 4) & 15u);
             }
             for (int j = jbeg; j <= jend; ++j) {
-              if (pre_w > 0) {
-                --pre_w;                             // requested before griddepcontrol.wait
-              } else {
-                mbar_wait(empty_w + 8 * ws, wph ^ 1u);
-                if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
-                else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
-                for (int ci = 0; ci < gs && !(p.debug & 1); ++ci)
-                  tma_load_2d(w0 + ws * p.w_stage_bytes + ci * CHUNK_BYTES, &S.mw, full_w + 8 * ws,
-                              j * S.cin + cc * KC, p.row0[gi][ci]);
-              }
+              mbar_wait(empty_w + 8 * ws, wph ^ 1u);
+              if (p.debug & 1) mbar_arrive(full_w + 8 * ws);
+              else             mbar_expect_tx(full_w + 8 * ws, (uint32_t)gs * CHUNK_BYTES);
+              for (int ci = 0; ci < gs && !(p.debug & 1); ++ci)
+                tma_load_2d(w0 + ws * p.w_stage_bytes + ci * CHUNK_BYTES, &S.mw, full_w + 8 * ws,
+                            j * S.cin + cc * KC, p.row0[gi][ci]);
               if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
             }
           }

@@ -255,32 +255,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // Filters are constants: the producer requests the first filter stages of this pair's first tile BEFORE waiting for
-  // the previous grid, so their latency runs under that grid's tail.  Dense batches only (the ragged tile list needs `live`).
-  const int n_cchunks = p.cin / KC;
-  uint32_t pre_w = 0;                               // filter stages requested ahead (producer thread only)
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mx) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
-    if (p.ep.live == nullptr && pair < p.ntiles) {
-      const uint32_t lead_full_w = map_to_cta(full_w, 0);
-      const int wrow = p.wrow[pair % p.npieces][rank];
-      for (int cc = 0; cc < n_cchunks && pre_w < (uint32_t)p.w_stages; ++cc)
-        for (int j = 0; j < p.k && pre_w < (uint32_t)p.w_stages; j += p.tg, ++pre_w) {
-          if (leader) mbar_expect_tx(full_w + 8 * pre_w, 2 * p.w_stage_bytes);
-          tma2_load_3d(w0 + pre_w * p.w_stage_bytes, &p.mw, lead_full_w + 8 * pre_w, cc * KC, wrow, j);
-        }
-    }
-  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.ep.live != nullptr) load_live_cache(p.ep, p.batch, live_s);
   if (bias_in_smem)
     for (int i = threadIdx.x; i < p.bias_words; i += blockDim.x) bias_s[i] = p.ep.bias[i];
   if (p.ep.live != nullptr || bias_in_smem) __syncthreads();
+  const int n_cchunks = p.cin / KC;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mx) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.mw) : "memory");
       const uint32_t lead_full_slab = map_to_cta(full_slab, 0), lead_full_w = map_to_cta(full_w, 0);
       const uint32_t slab_bytes = (uint32_t)p.slab_box_rows * ROW_BYTES;
       const int k = p.k, pad_left = p.pad_left, tg = p.tg;
@@ -301,13 +287,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
           // expect_tx, issue), which bounded every layer whose stage feeds fewer than ~400 cycles of MMAs
           // (profiles/r02_summary.md: a k = 3, 128 -> 128 layer took 61 us with neither MMAs nor epilogue).
           for (int j = 0; j < k; j += tg) {
-            if (pre_w > 0) {
-              --pre_w;                               // requested before griddepcontrol.wait
-            } else {
-              mbar_wait(empty_w + 8 * ws, wph ^ 1u);
-              if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * p.w_stage_bytes);
-              tma2_load_3d(w0 + ws * p.w_stage_bytes, &p.mw, lead_full_w + 8 * ws, cc * KC, wrow, j);
-            }
+            mbar_wait(empty_w + 8 * ws, wph ^ 1u);
+            if (leader) mbar_expect_tx(full_w + 8 * ws, 2 * p.w_stage_bytes);
+            tma2_load_3d(w0 + ws * p.w_stage_bytes, &p.mw, lead_full_w + 8 * ws, cc * KC, wrow, j);
             if (++ws == (uint32_t)p.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
