@@ -256,6 +256,40 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class Deadline:
+    """Safety net of the measurement itself: if a section does not finish in its time (a hung kernel or collective on any
+    rank), rank 0 prints the line with what was measured so far -- marked `incomplete` -- and every rank leaves.  A partial
+    line beats a ten-minute collective timeout that ends with none."""
+
+    def __init__(self, rank):
+        import threading
+        self._threading = threading
+        self.rank = rank
+        self.partial = None          # rank 0: the line so far; other ranks: {} once they have something to wait for
+        self._timer = None
+
+    def arm(self, seconds, what):
+        self.disarm()
+        self._timer = self._threading.Timer(seconds, self._fire, (seconds, what))
+        self._timer.daemon = True
+        self._timer.start()
+
+    def disarm(self):
+        if self._timer is not None:
+            self._timer.cancel()
+            self._timer = None
+
+    def _fire(self, seconds, what):
+        sys.stderr.write(f"bench.py: rank {self.rank}: '{what}' did not finish in {seconds} s -- giving up\n")
+        sys.stderr.flush()
+        if self.rank == 0 and self.partial:
+            line = dict(self.partial)
+            line["incomplete"] = f"'{what}' did not finish in {seconds} s; keys measured after it are absent"
+            sys.stdout.write(json.dumps(line) + "\n")
+            sys.stdout.flush()
+        os._exit(0 if self.partial is not None else 3)
+
+
 def run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM, slice_utts=64, reps=2):
     """configs[4]; every rank calls this.  Returns the result dict on rank 0, None elsewhere."""
     import torch
@@ -374,8 +408,11 @@ def run_ours(args, rank, local_rank, world):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
     def barrier():
+        # the device is drained BEFORE the collective is enqueued: a stuck kernel then shows up here (and in the Deadline
+        # below), not as a collective that every rank waits ten minutes for
+        torch.cuda.synchronize()
         if dist is not None:
-            dist.barrier()
+            dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
@@ -400,12 +437,27 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("QVC_BENCH_NO_SAMPLER") else None
     if sampler:
         sampler.start()
+    deadline = Deadline(rank)
+    deadline.arm(300, "device-resident timing")
 
     # ---- device-resident throughput ----
     l0 = capi.launch_count()
     ms, per = timed(lambda: net.infer(unit, mel, noise=noise), args.steps, args.warmup)
     launches = (capi.launch_count() - l0) // (args.steps + args.warmup)
     value = world * audio_s / (ms * 1e-3)
+    workload = ("BASELINE.json configs[1]: QuickVC SynthesizerTrn.infer, batch 64 x 10 s utterances, fp32 mode, "
+                "random-init weights, one 10 s target mel")
+    dtype_name = {"tf32": "tf32 operands, f32 accumulate/storage", "bf16": "bf16 operands, f32 accumulate",
+                  "fp16": "fp16 operands (10-bit mantissa, as TF32), f32 accumulate", "fp32": "f32"}[args.precision]
+    deadline.partial = {} if rank != 0 else {
+        "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype_name, "data": "synthetic",
+        "config": {"workload": workload, "batch_per_gpu": B, "frames": T, "mel_frames": TM, "precision": args.precision,
+                   "l2": "flushed (256 MB memset) between timed steps", "audio_seconds_per_step_per_gpu": audio_s},
+        "clocks": None, "e2e": None, "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+        "x_realtime_per_gpu": value / world, "step_ms_min_max": [min(per), max(per)]}
+    deadline.arm(240, "end-to-end timing (PipelinedConverter)")
 
     # ---- end to end through the public API: pinned host in, pinned host out, every step ----
     # quickvc_official_b200.pipeline.PipelinedConverter = H2D of unit + mel, net.infer(unit, mel), D2H of the waveform
@@ -441,14 +493,22 @@ def run_ours(args, rank, local_rank, world):
     # ---- BASELINE.json configs[4]: throughput sweep, 4096 utterances x 10 s sharded over the N GPUs (STRONG scaling: the
     # job is fixed), bf16 operands with fp32 accumulation, through quickvc_official_b200.shard.convert_sharded with the
     # gather of all waveforms to rank 0 (and their copy to pinned host memory there) inside the timed region.
+    if rank == 0:
+        deadline.partial["clocks"] = clocks
+        deadline.partial["e2e"] = {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e, "ms_per_step_regions": e2e_all,
+                                   "h2d_bytes_per_step": unit_h.numel() * 4 + mel_h.numel() * 4,
+                                   "d2h_bytes_per_step": wave_h.numel() * 4}
     sweep = None
     if args.sweep_utts > 0:
+        deadline.arm(480, "configs[4] sweep")
         sweep = run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM)
+    deadline.arm(900, "roofline / side measurements / CPU baseline")
 
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
+        deadline.disarm()
         return
 
     # ---- roofline of the dominant kernel: conv_tc_kernel, the tcgen05 series convolution (99.9 % of the
@@ -536,6 +596,7 @@ def run_ours(args, rank, local_rank, world):
     }
     if sweep is not None:
         line["sweep_4096_bf16"] = sweep
+    deadline.partial = line                       # from here on the safety net prints the full line with whatever keys it has
 
     if not args.no_extras and world == 1:
         # the fused post-net convolution + iSTFT / overlap-add / synthesis kernel (post_tail.cu) alone, on the HBM roofline of
@@ -692,6 +753,7 @@ def run_ours(args, rank, local_rank, world):
                                 "sample": f"{sample} x {T / 50:.0f} s utterances per call, {desc} (fp32, "
                                           f"torch.set_num_threads({cores})), 1 warm-up + 3 timed calls of {sec:.2f} s, "
                                           f"CPU {cpu_model_name()}"}
+    deadline.disarm()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
