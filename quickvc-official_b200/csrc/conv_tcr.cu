@@ -581,10 +581,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) conv_tc
 
   tc_fence_before();
   __syncthreads();
-  // execution barrier only (the peer may still multicast into / arrive on this CTA's barriers): the release form would
-  // first drain every global store of the CTA (MEMBAR.ALL.GPU: 10 % of the stall samples of a memory-bound layer)
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  // Release / acquire, not the relaxed form: the peer's epilogue warps arrive REMOTELY (and relaxed) on this CTA's
+  // tmem_empty barriers, and this CTA's shared memory is handed to the next grid's CTA the moment it exits -- the release
+  // of the cluster barrier is what guarantees that every such remote arrive has landed before that.  (A relaxed execution
+  // barrier was tried: it saved the MEMBAR at the end, ~1 us per launch, and left a remote arrive free to land in the
+  // NEXT kernel's freshly initialised barrier.)
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BUF_COLS) : "memory");

@@ -356,8 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) post_ta
 
   tc_fence_before();
   __syncthreads();
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  cluster_sync_all();       // release / acquire: the peer's remote tmem_empty arrives have landed before this CTA's shared memory is reused
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * PT_BUF_COLS) : "memory");
