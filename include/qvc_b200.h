@@ -368,6 +368,11 @@ uint64_t qvc_launch_count(void);
 /* name of the kernel the calling thread launched last through the library ("" before the first launch): lets a test
  * assert WHICH kernel served a call (e.g. "conv_tcr_kernel" for the frames-on-rows pair kernel). */
 const char* qvc_last_kernel(void);
+/* Page-locks / releases a host range the caller owns (cudaHostRegister, portable): the multi-GPU host gather registers one
+ * buffer shared by the ranks of a box in each of them (quickvc-official_b200/shard.py).  A failure is reported here and
+ * leaves no pending error behind in the caller's own CUDA runtime. */
+int qvc_host_register(void* ptr, size_t bytes);
+int qvc_host_unregister(void* ptr);
 /* 0 when device `dev` is an sm_100 part this library has code for. */
 int qvc_check_device(int dev);
 /* Measurement aid (bench.py's roofline): while enabled, every tcgen05 series-convolution launch is

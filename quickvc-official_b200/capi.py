@@ -120,6 +120,8 @@ SYMBOLS = {
     "qvc_launch_count": (C.c_uint64, []),
     "qvc_last_kernel": (C.c_char_p, []),
     "qvc_check_device": (C.c_int, [C.c_int]),
+    "qvc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "qvc_host_unregister": (C.c_int, [C.c_void_p]),
     "qvc_profile": (C.c_int, [C.c_int]),
     "qvc_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }

@@ -195,6 +195,28 @@ extern "C" int qvc_abi_version(void) { return QVC_ABI_VERSION; }
 extern "C" uint64_t qvc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* qvc_last_kernel(void) { return g_last_kernel; }
 
+extern "C" int qvc_host_register(void* ptr, size_t bytes) {
+  QVC_REQUIRE(ptr != nullptr && bytes > 0, "qvc_host_register: empty range");
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();                      // do not leave the error pending for the next launch check
+    set_error("qvc_host_register: cudaHostRegister(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+    return QVC_ERR_CUDA;
+  }
+  return QVC_OK;
+}
+
+extern "C" int qvc_host_unregister(void* ptr) {
+  QVC_REQUIRE(ptr != nullptr, "qvc_host_unregister: null pointer");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("qvc_host_unregister: cudaHostUnregister -> %s", cudaGetErrorString(e));
+    return QVC_ERR_CUDA;
+  }
+  return QVC_OK;
+}
+
 extern "C" int qvc_check_device(int dev) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

@@ -82,15 +82,20 @@ class HostGather:
             dist.barrier(group=group)
         self.flat = torch.from_file(self.path, shared=True, size=numel, dtype=torch.float32)
         self.host = self.flat[: n * samples].view(n, 1, samples)
+        # page-locked in every rank through the library (a failure there -- e.g. a locked-memory limit -- leaves the copies
+        # correct, only synchronous, and no error pending in torch's CUDA runtime)
         self._registered = False
         if torch.cuda.is_available():
-            rc = torch.cuda.cudart().cudaHostRegister(self.flat.data_ptr(), numel * 4, 0)
-            self._registered = int(rc) == 0
+            from . import capi
+            torch.cuda.current_device()                # make sure this process has a CUDA context
+            self._registered = capi.load().qvc_host_register(self.flat.data_ptr(), numel * 4) == 0
         self._copy_stream = None
 
     def close(self) -> None:
         if self._registered:
-            torch.cuda.cudart().cudaHostUnregister(self.flat.data_ptr())
+            from . import capi
+            torch.cuda.synchronize()
+            capi.load().qvc_host_unregister(self.flat.data_ptr())
             self._registered = False
         if self.world > 1:
             dist.barrier(group=self.group)
