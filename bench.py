@@ -261,8 +261,11 @@ class Deadline:
     rank), rank 0 prints the line with what was measured so far -- marked `incomplete` -- and every rank leaves.  A partial
     line beats a ten-minute collective timeout that ends with none."""
 
+    current = None               # the instance of this process (main()'s exception path reads its partial line)
+
     def __init__(self, rank):
         import threading
+        Deadline.current = self
         self._threading = threading
         self.rank = rank
         self.partial = None          # rank 0: the line so far; other ranks: {} once they have something to wait for
@@ -501,7 +504,16 @@ def run_ours(args, rank, local_rank, world):
     sweep = None
     if args.sweep_utts > 0:
         deadline.arm(480, "configs[4] sweep")
-        sweep = run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM)
+        if world > 1:
+            sweep = run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM)
+        else:
+            try:                                   # one rank: nobody waits in a collective, so a failure costs this key only
+                sweep = run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM)
+            except Exception as exc:               # noqa: BLE001
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                sweep = {"failed": f"{type(exc).__name__}: {exc}"[:400]}
+                torch.cuda.empty_cache()
     deadline.arm(900, "roofline / side measurements / CPU baseline")
 
     if rank != 0:
@@ -598,7 +610,20 @@ def run_ours(args, rank, local_rank, world):
         line["sweep_4096_bf16"] = sweep
     deadline.partial = line                       # from here on the safety net prints the full line with whatever keys it has
 
-    if not args.no_extras and world == 1:
+    def section(name, fn):
+        # a side measurement that fails (or a box that cannot run it) costs its own key, never the headline line
+        try:
+            fn()
+        except Exception as exc:      # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            line.setdefault("failed_sections", {})[name] = f"{type(exc).__name__}: {exc}"[:400]
+            try:
+                torch.cuda.synchronize()
+            except Exception:         # noqa: BLE001
+                pass
+
+    def extra_tail():
         # the fused post-net convolution + iSTFT / overlap-add / synthesis kernel (post_tail.cu) alone, on the HBM roofline of
         # SURVEY.md section 8d's fused definition: the 128-channel operand series in, the waveform out
         frames_post = 20 * T + 1
@@ -631,7 +656,8 @@ def run_ours(args, rank, local_rank, world):
                 "note": "measured issue-bound (polar + DFT + 272 FMAs of synthesis FIR per sub-band sample on 8 epilogue warps), "
                         "not HBM-bound: profiles/r02_summary.md",
                 "peak_source": pk["source"]}
-        # the separately reported bf16 mode, and the p50 latency of one 5 s clip
+    def extra_modes():
+        # the separately reported bf16 / fp16 / strict-fp32 modes
         if args.precision == "tf32":
             nb = make_net("bf16")
             ms_b, _ = timed(lambda: nb.infer(unit, mel, noise=noise), max(3, args.steps // 2), 2)
@@ -654,6 +680,7 @@ def run_ours(args, rank, local_rank, world):
                                         "note": "exact fp32 FMA kernels (waveform max-abs 1.5e-7 vs the reference); not the "
                                                 "product path, kept to validate the tensor-core one"}
             del nf
+    def extra_decoder():
         # ---- BASELINE.json configs[2]: the decoder alone (Multistream_iSTFT_Generator: conv_pre, ConvTranspose / MRF
         # ResBlocks, conv_post, fused iSTFT / OLA / sub-band synthesis) at batch 256 x 10 s, through net.decode(z, g)
         DEC_B = 256
@@ -679,6 +706,7 @@ def run_ours(args, rank, local_rank, world):
         del z256
         torch.cuda.empty_cache()
 
+    def extra_latency():
         # ---- single-call latency: the 5 s clip of the metric, and BASELINE.json configs[3] (0.5 s chunks, batch 1) in the
         # fp32 mode (tf32), fp16 and bf16: p50 / p99 over 1000 calls each, through infer(unit, mel) as convert.py calls it
         # and with the target-speaker embedding cached (the reference recomputes it on every call, models.py:635)
@@ -715,6 +743,7 @@ def run_ours(args, rank, local_rank, world):
             entry.update(entry[args.precision if args.precision in entry else "tf32"])      # top-level p50 / p99: this run's mode
             line[name] = entry
 
+    def extra_ragged():
         # SURVEY.md section 8f "next" #3: ragged batches -- the same B utterances with lengths drawn from 5 .. 10 s, sorted
         # as the conversion driver does, padded to the longest; the rate counts live audio only
         lens = torch.sort(torch.randint(T // 2, T + 1, (B,), generator=torch.Generator().manual_seed(3))).values
@@ -728,6 +757,7 @@ def run_ours(args, rank, local_rank, world):
                                         "exactly the samples of its own single-utterance call (tests/test_gpu_ragged.py); "
                                         "tiles wholly past an utterance's end are skipped by every warp role"}
 
+    def extra_mel():
         # SURVEY.md section 8f "next" #1: the target-mel front end (wave_to_mel, convert.py:75-77) for one 10 s target
         from quickvc_official_b200 import mel as qmel
         from oracle import mel_oracle
@@ -746,13 +776,21 @@ def run_ours(args, rank, local_rank, world):
                                         "GEMM (1.66 GFLOP) + magnitude + Slaney mel + log; latency bound (500 frames); CPU = "
                                         "torch.stft oracle on the host threads"}
 
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_extras and world == 1:
+        for name, fn in (("tail_roofline", extra_tail), ("precision_modes", extra_modes), ("decoder_only_b256", extra_decoder),
+                         ("latency", extra_latency), ("ragged_batch", extra_ragged), ("mel_frontend", extra_mel)):
+            section(name, fn)
+
+    def cpu_baseline():
         cores = os.cpu_count() or 1
         rate, sec, sample, kind, desc = cpu_infer_rate(sd, cfg, T, TM, 1, 3, budget_s=args.cpu_baseline_budget_s, max_batch=B)
         line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": kind,
                                 "sample": f"{sample} x {T / 50:.0f} s utterances per call, {desc} (fp32, "
                                           f"torch.set_num_threads({cores})), 1 warm-up + 3 timed calls of {sec:.2f} s, "
                                           f"CPU {cpu_model_name()}"}
+
+    if not args.no_cpu_baseline and world == 1:
+        section("cpu_baseline", cpu_baseline)
     deadline.disarm()
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -767,8 +805,25 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
-    else:
+        return
+    try:
         run_ours(args, rank, local_rank, world)
+    except Exception:      # noqa: BLE001
+        # a failure after the headline was measured still ends with that line on stdout (marked `incomplete`) and rc 0; the
+        # other ranks of a multi-GPU run then leave through their own deadline.  Before it, the failure is the result.
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        sys.stderr.flush()
+        d = Deadline.current
+        if d is not None and d.partial is not None:
+            d.disarm()
+            if rank == 0 and d.partial:
+                line = dict(d.partial)
+                line["incomplete"] = "an exception ended the run after these keys were measured (traceback on stderr)"
+                sys.stdout.write(json.dumps(line) + "\n")
+                sys.stdout.flush()
+            os._exit(0)
+        raise
 
 
 if __name__ == "__main__":

@@ -59,3 +59,35 @@ def test_disarmed_deadline_does_nothing():
         print("done")
     ''')
     assert r.returncode == 0 and r.stdout.strip() == "done"
+
+
+def test_exception_after_the_headline_still_prints_the_line():
+    r = _run('''
+        import sys, bench
+        def boom(args, rank, local_rank, world):
+            d = bench.Deadline(rank)
+            d.partial = {"metric": "audio-sec/sec", "value": 3.0, "e2e": None}
+            d.arm(60, "end-to-end timing")
+            raise RuntimeError("copy failed")
+        bench.run_ours = boom
+        sys.argv = ["bench.py"]
+        bench.main()
+        print("not reached")
+    ''')
+    assert r.returncode == 0 and "not reached" not in r.stdout
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] == 3.0 and "exception" in line["incomplete"]
+    assert "RuntimeError: copy failed" in r.stderr
+
+
+def test_exception_before_any_measurement_is_the_result():
+    r = _run('''
+        import sys, bench
+        def boom(args, rank, local_rank, world):
+            bench.Deadline(rank)
+            raise RuntimeError("no device")
+        bench.run_ours = boom
+        sys.argv = ["bench.py"]
+        bench.main()
+    ''')
+    assert r.returncode != 0 and r.stdout.strip() == "" and "RuntimeError: no device" in r.stderr
