@@ -75,6 +75,26 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(capi.Model) == 16 + (2 * 114 + 5) * 40 + 24 + 11 * 8 + 4 * 8
 
 
+def test_plain_c_consumer_binds_the_abi(tmp_path):
+    """include/qvc_b200.h is a C header (C99, -pedantic -Werror) and the library is usable from plain C with no Python, torch
+    or CUDA headers: tests/c/consumer.c dlopens it, checks the ABI version and size queries, and gets the fold's QVC_ERR_ARG
+    + error string for a misshapen state_dict entry.  The struct sizes the C compiler derives from the header are the ones
+    the ctypes mirror (capi.py) uses."""
+    import subprocess
+    exe = str(tmp_path / "consumer")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "consumer.c"), "-o", exe, "-ldl"], check=True)
+    r = subprocess.run([exe, capi.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert f"ok abi={capi.QVC_ABI_VERSION} " in r.stdout and "enc_p.pre.weight" in r.stdout
+    sizes = dict(kv.split("=") for kv in next(l for l in r.stdout.splitlines() if l.startswith("sizeof ")).split()[1:])
+    mirror = {"qvc_tensor": capi.Tensor, "qvc_epi_segment": capi.EpiSegment, "qvc_conv_args": capi.ConvArgs,
+              "qvc_spk_weights": capi.SpkWeights, "qvc_mel_weights": capi.MelWeights, "qvc_tail_weights": capi.TailWeights,
+              "qvc_layer": capi.Layer, "qvc_model": capi.Model, "qvc_state_entry": capi.StateEntry, "qvc_taps": capi.Taps}
+    for name, cls in mirror.items():
+        assert int(sizes[name]) == ctypes.sizeof(cls), (name, sizes[name], ctypes.sizeof(cls))
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted")
 def test_seeded_init_equals_reference(model_cfg):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
