@@ -110,6 +110,9 @@ def install():
         def submit(self, unit_h, mel_h, noise=None):
             if os.environ.get("QVC_FAKE_FAIL") == "e2e_rank1" and os.environ.get("RANK") == "1":
                 raise RuntimeError("injected failure on rank 1")
+            if os.environ.get("QVC_FAKE_FAIL") == "hang_rank1" and os.environ.get("RANK") == "1":
+                import time
+                time.sleep(3600)                                   # a kernel that never finishes
             return self.net.infer(unit_h, mel_h), FakeEvent()
 
         def drain(self):

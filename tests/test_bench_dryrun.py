@@ -108,3 +108,19 @@ def test_a_rank_that_fails_after_the_headline_leaves_a_partial_line(tmp_path):
     # deadline fires: either way the partial line is what ends the run
     assert "end-to-end timing" in line["incomplete"] or "exception" in line["incomplete"]
     assert "injected failure on rank 1" in r.stderr
+
+
+def test_a_rank_that_hangs_ends_with_the_partial_line_at_the_deadline(tmp_path):
+    """The 8-GPU incident of round 2 (profiles/r02_n8_incident.log), replayed: one rank never leaves the end-to-end section.
+    Every rank gives up at the section's deadline, rank 0 with the headline it had already measured."""
+    script = tmp_path / "dry.py"
+    script.write_text(DRIVER)
+    port = 29500 + (os.getpid() + 13) % 400
+    env = dict(os.environ, QVC_FAKE_FAIL="hang_rank1", QVC_BENCH_DEADLINE_SCALE="0.03")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), str(script), "--gpus", "2"] + SMALL,
+                       capture_output=True, text=True, cwd=ROOT, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = _line(r.stdout)
+    assert line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"] is None
+    assert "end-to-end timing" in line["incomplete"] and "did not finish" in r.stderr
