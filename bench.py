@@ -442,7 +442,7 @@ def run_ours(args, rank, local_rank, world):
     if sampler:
         sampler.start()
     deadline = Deadline(rank)
-    deadline.arm(300, "device-resident timing")
+    deadline.arm(200, "device-resident timing")
 
     # ---- device-resident throughput ----
     l0 = capi.launch_count()
@@ -461,7 +461,7 @@ def run_ours(args, rank, local_rank, world):
                    "l2": "flushed (256 MB memset) between timed steps", "audio_seconds_per_step_per_gpu": audio_s},
         "clocks": None, "e2e": None, "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "x_realtime_per_gpu": value / world, "step_ms_min_max": [min(per), max(per)]}
-    deadline.arm(240, "end-to-end timing (PipelinedConverter)")
+    deadline.arm(180, "end-to-end timing (PipelinedConverter)")
 
     # ---- end to end through the public API: pinned host in, pinned host out, every step ----
     # quickvc_official_b200.pipeline.PipelinedConverter = H2D of unit + mel, net.infer(unit, mel), D2H of the waveform
@@ -504,7 +504,7 @@ def run_ours(args, rank, local_rank, world):
                                    "d2h_bytes_per_step": wave_h.numel() * 4}
     sweep = None
     if args.sweep_utts > 0:
-        deadline.arm(480, "configs[4] sweep")
+        deadline.arm(300, "configs[4] sweep")
         if world > 1:
             sweep = run_sweep(args, make_net, dev, rank, world, dist, barrier, T, TM)
         else:
