@@ -416,7 +416,7 @@ def run_ours(args, rank, local_rank, world):
         # below), not as a collective that every rank waits ten minutes for
         torch.cuda.synchronize()
         if dist is not None:
-            dist.barrier(device_ids=[local_rank])
+            dist.barrier()                 # device: the one bound at init_process_group(device_id=...)
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
