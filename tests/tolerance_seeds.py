@@ -8,7 +8,7 @@ on one 5 s utterance (BASELINE.json configs[0] shape).  The emulation rounds whe
 accumulation order.  The GPU suite holds the kernels themselves to the same bounds on two seeds at full size
 (tests/test_gpu_fullsize.py); this table is the wider, cheaper sweep behind the claim.
 
-    python scripts/tolerance_seeds.py [n_seeds] > profiles/r02_tolerance_seeds.md
+    python tests/tolerance_seeds.py [n_seeds] > profiles/r02_tolerance_seeds.md
 """
 import json
 import os
