@@ -75,6 +75,26 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(capi.Model) == 16 + (2 * 114 + 5) * 40 + 24 + 11 * 8 + 4 * 8
 
 
+def test_integration_md_binding_stub_is_valid_python_against_the_real_binding():
+    """The ctypes stub INTEGRATION.md shows a maintainer compiles, and every `_lib.` / `capi.` name it uses exists."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, re.S)
+    stub = next(b for b in blocks if "class B200Infer" in b)
+    compile(stub, "INTEGRATION.md", "exec")
+    for sym in set(re.findall(r"_lib\.(qvc_[a-z0-9_]+)", stub)):
+        assert sym in capi.SYMBOLS, sym
+    for attr in set(re.findall(r"capi\.([A-Za-z_][A-Za-z0-9_]*)", stub)):
+        assert hasattr(capi, attr), attr
+    # the argument counts of the two calls it makes match the bound prototypes
+    for sym in ("qvc_prepare_weights", "qvc_infer"):
+        call = re.search(sym + r"\((.*?)\)(?:,\s*\"|\n\s+capi\.check)", stub, re.S).group(1)
+        depth, n = 0, 1
+        for ch in call:
+            depth += ch in "([" ; depth -= ch in ")]"
+            n += ch == "," and depth == 0
+        assert n == len(capi.SYMBOLS[sym][1]), (sym, n, len(capi.SYMBOLS[sym][1]))
+
+
 def test_plain_c_consumer_binds_the_abi(tmp_path):
     """include/qvc_b200.h is a C header (C99, -pedantic -Werror) and the library is usable from plain C with no Python, torch
     or CUDA headers: tests/c/consumer.c dlopens it, checks the ABI version and size queries, and gets the fold's QVC_ERR_ARG
